@@ -1,0 +1,25 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def orc():
+    """The CPU oracle (oracle/liboracle.so), built on demand with gcc."""
+    from oracle import oracle
+
+    oracle.build()
+    oracle.lib()
+    return oracle
+
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
