@@ -1,0 +1,146 @@
+/*
+ * splat.h -- C ABI of libsplat_b200: a B200 (sm_100a) Gaussian-splat rasteriser that drops in
+ * behind thomasantony/splat's render entry point.
+ *
+ * Replaces (reference paths relative to /root/reference/src):
+ *   GaussianSplatPipeline01::render_to_buffer   pipelines.rs:66-86
+ *   GaussianSplatPipeline02::render_to_buffer   pipelines.rs:260-280
+ * and everything those call per frame: sort_gaussians / GaussianList::sort
+ * (gaussians.rs:297-306, :464-471), the euc Pipeline callbacks vertex / fragment / blend
+ * (pipelines.rs:96-168, :184-256), gaussian_vertex_shader (:17-51), project_cov3d_to_screen
+ * (gaussians.rs:114-161, :473-522), eval_spherical_harmonics (:41-99), compute_cov3d
+ * (:101-113, :446-462), and the euc 0.6.0 rasteriser loop itself (Cargo.lock:221-229).
+ *
+ * Plain C: opaque context, plain pointers and sizes, int error codes; nothing throws or aborts
+ * across this boundary.  The Rust side binds it with bindgen; tests and
+ * bench.py bind it with ctypes (splat_b200/_lib.py).
+ *
+ * Threading: one render at a time per context (not re-entrant); distinct contexts are
+ * independent.  All host pointers are borrowed for the duration of the call only.
+ */
+#ifndef SPLAT_B200_H
+#define SPLAT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPLAT_ABI_VERSION 1u
+
+typedef struct splat_ctx splat_ctx;
+
+enum {
+  SPLAT_OK = 0,
+  SPLAT_ERR_INVALID = -1,     /* bad argument (null pointer, zero size, misaligned stripe ...)  */
+  SPLAT_ERR_CUDA = -2,        /* a CUDA runtime call failed; see splat_last_error               */
+  SPLAT_ERR_NOMEM = -3,       /* host or device allocation failed                               */
+  SPLAT_ERR_UNSUPPORTED = -4, /* e.g. camera.w/h differ from the target size, tile != 16        */
+  SPLAT_ERR_STATE = -5        /* render before upload                                           */
+};
+
+/* Behaviour switches.  lowpass selects which reference pipeline is reproduced; the three
+ * euc-semantics switches mirror the assumptions E1/E3 of SURVEY.md section 8c and must match
+ * the oracle's orc_config for parity. */
+typedef struct {
+  int32_t  device;         /* CUDA device ordinal                                                */
+  float    lowpass;        /* 0.01 = Pipeline01 (gaussians.rs:156-157), 0.3 = Pipeline02 (:517-518) */
+  int32_t  y_down;         /* 1: NDC +y is the bottom row (euc CoordinateMode::VULKAN default)    */
+  int32_t  zclip_mode;     /* 0: keep 0<=z<1, 1: keep -1<=z<1, 2: no z clip                       */
+  float    sample_offset;  /* pixel sample point (x+off, y+off); 0.5                             */
+  uint32_t tile;           /* screen tile edge in pixels; only 16 is built                       */
+  uint64_t max_instances;  /* initial capacity of the tile-instance buffers (0 = auto, grows)    */
+} splat_config;
+
+/* What the kernels need from `Camera` (camera.rs:4-19): the two matrices exactly as nalgebra
+ * stores them (column-major), the *field* `position` (camera.rs:10 -- never updated by
+ * orbiting, and the SH view direction uses it, pipelines.rs:99), w/h and
+ * get_htanfovxy_focal() (camera.rs:84-89). */
+typedef struct {
+  float view[16];     /* camera.get_view_matrix().as_slice()    */
+  float proj[16];     /* camera.get_project_matrix().as_slice() */
+  float position[3];  /* camera.position                        */
+  float w, h;         /* camera.w, camera.h                     */
+  float htanx, htany, focal; /* camera.get_htanfovxy_focal()    */
+} splat_camera;
+
+/* Per-stage device times of the last completed render (CUDA events) and its work counters. */
+typedef struct {
+  float    project_ms;   /* K1 project                                         */
+  float    sort_ms;      /* K3 depth radix sort + tile radix sort              */
+  float    bin_ms;       /* K2 count/scan/emit + K4 tile ranges                */
+  float    blend_ms;     /* K5 blend                                           */
+  float    total_ms;     /* first kernel to last kernel                        */
+  float    h2d_ms;       /* framebuffer upload (host-buffer entry points only) */
+  float    d2h_ms;       /* framebuffer download                               */
+  uint32_t frames_retried; /* renders repeated because the instance buffers had to grow */
+  uint64_t n_gaussians;
+  uint64_t n_visible;    /* Gaussians that pass the z clip and the degeneracy guard */
+  uint64_t n_instances;  /* (tile, Gaussian) pairs                                  */
+  uint64_t n_tiles;      /* tiles in the rendered stripe                            */
+  uint64_t kernel_launches; /* kernels launched by the last render                  */
+} splat_timings;
+
+uint32_t    splat_abi_version(void);
+void        splat_config_default(splat_config *cfg);
+int         splat_create(splat_ctx **out, const splat_config *cfg);
+void        splat_destroy(splat_ctx *ctx);
+const char *splat_last_error(const splat_ctx *ctx);
+
+/* Scene upload, GaussianList layout (gaussians.rs:408-416; from_vec :419-440): each array is
+ * the contiguous column-major nalgebra matrix -- pos4 4xN (x,y,z,1), scale3 3xN (already
+ * exp'd), opacity N (already sigmoid'd), rot_xyzw 4xN (nalgebra coords order i,j,k,w,
+ * un-normalised is fine), sh48 48xN.  Host pointers.  Copies to the device, computes cov3d
+ * there (compute_cov3d, gaussians.rs:446-462) and repacks to the device layout. */
+int splat_upload_soa(splat_ctx *ctx, const float *pos4, const float *scale3, const float *opacity,
+                     const float *rot_xyzw, const float *sh48, uint64_t n);
+
+/* Scene upload for Pipeline01's Vec<Gaussian> (gaussians.rs:31-38).  The Rust struct is not
+ * repr(C), so the shim copies each Gaussian into 59 consecutive floats:
+ * position[3] scale[3] opacity rotation_xyzw[4] sh[48]. */
+int splat_upload_aos(splat_ctx *ctx, const float *gaussians59, uint64_t n);
+
+/* render_to_buffer.  fb_inout: W*H pixels, row-major, 0xAARRGGBB (euc::Buffer<u32,2>::raw(),
+ * main.rs:79), blended onto (the caller clears it, main.rs:73) and overwritten.  Synchronous:
+ * host->device copy of fb, all kernels, device->host copy.  Requires camera.w == W and
+ * camera.h == H (true for every caller in the reference). */
+int splat_render(splat_ctx *ctx, const splat_camera *cam, uint32_t *fb_inout, uint32_t W, uint32_t H);
+
+/* Same for a horizontal stripe of rows [row0,row1) of the W x H image (multi-GPU sharding by
+ * screen-tile stripes): fb_rows points at row row0 and holds (row1-row0)*W pixels.  row0 must
+ * be a multiple of the tile size; row1 a multiple of it or == H. */
+int splat_render_rows(splat_ctx *ctx, const splat_camera *cam, uint32_t *fb_rows, uint32_t W,
+                      uint32_t H, uint32_t row0, uint32_t row1);
+
+/* Device-buffer variant: fb_rows_dev is a device pointer on cfg.device (e.g. the slice of an
+ * NCCL-registered gather buffer); work is enqueued on `stream` (a cudaStream_t, NULL = the
+ * context's own stream).  The call blocks once mid-frame to read the tile-instance count
+ * (8 bytes) and returns after enqueueing the remaining kernels, without waiting for them. */
+int splat_render_device(splat_ctx *ctx, const splat_camera *cam, void *fb_rows_dev, uint32_t W,
+                        uint32_t H, uint32_t row0, uint32_t row1, void *stream);
+
+/* Blocks until the last enqueued render finished, then reports its stage times. */
+int splat_get_timings(splat_ctx *ctx, splat_timings *out);
+
+/* Pin / unpin a caller-owned host buffer (cudaHostRegister) so that the framebuffer copies of
+ * splat_render run at full PCIe rate; e.g. the Rust shim pins `color.raw_mut()` once. */
+int splat_pin_host(void *p, uint64_t bytes);
+int splat_unpin_host(void *p);
+
+/* Debug / parity taps (tests only).
+ * splat_debug_project runs K1 alone for the full frame and copies out, per Gaussian:
+ *   records12: 12 floats (cxp cyp A B | C opacity hx hy | r g b power_threshold), zeros if culled;
+ *   depth_keys: u32 sort key (0xFFFFFFFF = culled); tile_rects4: 4 x u16 (x0 y0 x1 y1, inclusive).
+ * splat_debug_read_order returns the depth order (Gaussian indices far -> near) of the last render.
+ * splat_debug_sort_pairs sorts host (key,value) arrays in place on bits [0,bits) with the device
+ * radix sort. */
+int splat_debug_project(splat_ctx *ctx, const splat_camera *cam, uint32_t W, uint32_t H,
+                        float *records12, uint32_t *depth_keys, uint32_t *tile_rects4);
+int splat_debug_read_order(splat_ctx *ctx, uint32_t *order, uint64_t cap, uint64_t *n_visible);
+int splat_debug_sort_pairs(splat_ctx *ctx, uint32_t *keys, uint32_t *vals, uint64_t n, int bits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPLAT_B200_H */

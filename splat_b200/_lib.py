@@ -1,0 +1,188 @@
+"""ctypes binding of libsplat_b200.so -- the same C ABI (include/splat.h) the Rust shim binds
+with bindgen.  There is no fallback: if the CUDA library is missing or fails to load, importing
+a render entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsplat_b200.so")
+
+SPLAT_OK = 0
+ERRORS = {-1: "SPLAT_ERR_INVALID", -2: "SPLAT_ERR_CUDA", -3: "SPLAT_ERR_NOMEM",
+          -4: "SPLAT_ERR_UNSUPPORTED", -5: "SPLAT_ERR_STATE"}
+
+# every symbol include/splat.h declares (tests/test_abi.py checks the header against this list)
+EXPORTS = ["splat_abi_version", "splat_config_default", "splat_create", "splat_destroy",
+           "splat_last_error", "splat_upload_soa", "splat_upload_aos", "splat_render",
+           "splat_render_rows", "splat_render_device", "splat_get_timings", "splat_pin_host",
+           "splat_unpin_host", "splat_debug_project", "splat_debug_read_order",
+           "splat_debug_sort_pairs"]
+
+
+class SplatConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("lowpass", C.c_float), ("y_down", C.c_int32),
+                ("zclip_mode", C.c_int32), ("sample_offset", C.c_float), ("tile", C.c_uint32),
+                ("max_instances", C.c_uint64)]
+
+
+class SplatCamera(C.Structure):
+    _fields_ = [("view", C.c_float * 16), ("proj", C.c_float * 16), ("position", C.c_float * 3),
+                ("w", C.c_float), ("h", C.c_float),
+                ("htanx", C.c_float), ("htany", C.c_float), ("focal", C.c_float)]
+
+
+class SplatTimings(C.Structure):
+    _fields_ = [("project_ms", C.c_float), ("sort_ms", C.c_float), ("bin_ms", C.c_float),
+                ("blend_ms", C.c_float), ("total_ms", C.c_float), ("h2d_ms", C.c_float),
+                ("d2h_ms", C.c_float), ("frames_retried", C.c_uint32),
+                ("n_gaussians", C.c_uint64), ("n_visible", C.c_uint64), ("n_instances", C.c_uint64),
+                ("n_tiles", C.c_uint64), ("kernel_launches", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class SplatError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """dlopen the CUDA library; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    fp, u32p, vp = C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.c_void_p
+    L.splat_abi_version.restype = C.c_uint32
+    L.splat_config_default.argtypes = [C.POINTER(SplatConfig)]
+    L.splat_config_default.restype = None
+    L.splat_create.argtypes = [C.POINTER(vp), C.POINTER(SplatConfig)]
+    L.splat_destroy.argtypes = [vp]
+    L.splat_destroy.restype = None
+    L.splat_last_error.argtypes = [vp]
+    L.splat_last_error.restype = C.c_char_p
+    L.splat_upload_soa.argtypes = [vp, fp, fp, fp, fp, fp, C.c_uint64]
+    L.splat_upload_aos.argtypes = [vp, fp, C.c_uint64]
+    L.splat_render.argtypes = [vp, C.POINTER(SplatCamera), vp, C.c_uint32, C.c_uint32]
+    L.splat_render_rows.argtypes = [vp, C.POINTER(SplatCamera), vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.splat_render_device.argtypes = [vp, C.POINTER(SplatCamera), vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp]
+    L.splat_get_timings.argtypes = [vp, C.POINTER(SplatTimings)]
+    L.splat_pin_host.argtypes = [vp, C.c_uint64]
+    L.splat_unpin_host.argtypes = [vp]
+    L.splat_debug_project.argtypes = [vp, C.POINTER(SplatCamera), C.c_uint32, C.c_uint32, vp, vp, vp]
+    L.splat_debug_read_order.argtypes = [vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.splat_debug_sort_pairs.argtypes = [vp, vp, vp, C.c_uint64, C.c_int]
+    for name in EXPORTS:
+        getattr(L, name)  # AttributeError if the .so does not export it
+    _lib = L
+    return L
+
+
+def camera_struct(camera) -> SplatCamera:
+    """Marshal a splat_b200.camera.Camera exactly like the Rust shim does."""
+    cam = SplatCamera()
+    v = np.asarray(camera.get_view_matrix(), np.float32).T.reshape(-1)   # column-major
+    p = np.asarray(camera.get_project_matrix(), np.float32).T.reshape(-1)
+    hf = camera.get_htanfovxy_focal()
+    for i in range(16):
+        cam.view[i] = float(v[i])
+        cam.proj[i] = float(p[i])
+    for i in range(3):
+        cam.position[i] = float(camera.position[i])
+    cam.w, cam.h = float(camera.w), float(camera.h)
+    cam.htanx, cam.htany, cam.focal = float(hf[0]), float(hf[1]), float(hf[2])
+    return cam
+
+
+def _fp(a):
+    assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class Context:
+    """Owns one splat_ctx (one GPU)."""
+
+    def __init__(self, device=0, lowpass=0.3, y_down=1, zclip_mode=0, sample_offset=0.5, max_instances=0):
+        self.L = load()
+        cfg = SplatConfig()
+        self.L.splat_config_default(C.byref(cfg))
+        cfg.device, cfg.lowpass, cfg.y_down = device, lowpass, y_down
+        cfg.zclip_mode, cfg.sample_offset, cfg.max_instances = zclip_mode, sample_offset, max_instances
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        rc = self.L.splat_create(C.byref(self.h), C.byref(cfg))
+        if rc:
+            raise SplatError(rc, "splat_create failed")
+        self.n = 0
+
+    def _check(self, rc):
+        if rc:
+            raise SplatError(rc, self.L.splat_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.splat_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def upload(self, g):
+        """g: GaussianList-shaped (positions, scales, opacities, rotations, sh)."""
+        self._check(self.L.splat_upload_soa(self.h, _fp(g.positions), _fp(g.scales), _fp(g.opacities),
+                                            _fp(g.rotations), _fp(g.sh), g.positions.shape[0]))
+        self.n = g.positions.shape[0]
+
+    def upload_aos(self, g59: np.ndarray):
+        self._check(self.L.splat_upload_aos(self.h, _fp(g59), g59.shape[0]))
+        self.n = g59.shape[0]
+
+    def render(self, cam: SplatCamera, fb: np.ndarray, row0=0, row1=None):
+        """fb: uint32 (rows, W) host array holding rows [row0,row1) of the H x W image."""
+        assert fb.dtype == np.uint32 and fb.flags["C_CONTIGUOUS"]
+        H, W = int(cam.h), int(cam.w)
+        row1 = H if row1 is None else row1
+        assert fb.shape == (row1 - row0, W)
+        self._check(self.L.splat_render_rows(self.h, C.byref(cam), fb.ctypes.data, W, H, row0, row1))
+
+    def render_ptr(self, cam: SplatCamera, host_ptr: int, W: int, H: int, row0=0, row1=None):
+        self._check(self.L.splat_render_rows(self.h, C.byref(cam), host_ptr, W, H, row0, H if row1 is None else row1))
+
+    def render_device(self, cam: SplatCamera, dev_ptr: int, W: int, H: int, row0=0, row1=None, stream=0):
+        self._check(self.L.splat_render_device(self.h, C.byref(cam), dev_ptr, W, H, row0,
+                                               H if row1 is None else row1, stream or None))
+
+    def timings(self) -> dict:
+        t = SplatTimings()
+        self._check(self.L.splat_get_timings(self.h, C.byref(t)))
+        return t.as_dict()
+
+    def debug_project(self, cam: SplatCamera):
+        H, W = int(cam.h), int(cam.w)
+        rec = np.zeros((self.n, 12), np.float32)
+        keys = np.zeros(self.n, np.uint32)
+        rects = np.zeros((self.n, 4), np.uint16)
+        self._check(self.L.splat_debug_project(self.h, C.byref(cam), W, H, rec.ctypes.data,
+                                               keys.ctypes.data, rects.ctypes.data))
+        return rec, keys, rects
+
+    def debug_order(self) -> np.ndarray:
+        order = np.zeros(max(self.n, 1), np.uint32)
+        nv = C.c_uint64()
+        self._check(self.L.splat_debug_read_order(self.h, order.ctypes.data, len(order), C.byref(nv)))
+        return order[: nv.value].copy()
+
+    def debug_sort_pairs(self, keys: np.ndarray, vals: np.ndarray, bits=32):
+        assert keys.dtype == np.uint32 and vals.dtype == np.uint32
+        self._check(self.L.splat_debug_sort_pairs(self.h, keys.ctypes.data, vals.ctypes.data, len(keys), bits))

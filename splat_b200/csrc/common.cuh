@@ -1,0 +1,54 @@
+// common.cuh -- shared declarations of the sm_100a splat rasteriser (product code).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace splat {
+
+constexpr int TILE = 16;                 // screen tile edge (pixels)
+constexpr int SCENE_PLANES = 10;         // float4 planes per Gaussian in the device scene
+constexpr uint32_t KEY_CULLED = 0xFFFFFFFFu;
+
+// Device scene layout (HBM, written once per upload by pack_scene_kernel):
+//   plane 0      : (x, y, z, opacity)
+//   planes 1..9  : 36 floats = cov3d[9] row-major followed by sh[0..26] (SH degrees 0..2)
+// Each plane is a dense float4[N] array, so a warp reading plane k for 32 consecutive
+// Gaussians issues one fully coalesced 512-byte request.  160 B per Gaussian.
+
+// Everything the kernels need to know about one frame; passed by value (__grid_constant__).
+struct FrameParams {
+  float view[16];      // column-major, camera.get_view_matrix()
+  float proj[16];      // column-major, camera.get_project_matrix()
+  float cam_pos[3];    // camera.position
+  float focal, htanx, htany;
+  float lowpass;
+  float sample_off;
+  float ysign;         // +1: y_down, -1: y-up
+  int zclip_mode;
+  uint32_t W, H;       // full image size in pixels
+  uint32_t row0, row1; // rendered stripe [row0,row1)
+  uint32_t tiles_x;    // ceil(W/16)
+  uint32_t tile_y0;    // first tile row of the stripe
+  uint32_t tiles_y;    // tile rows in the stripe
+  uint32_t n;          // Gaussians
+};
+
+// Splat record produced by project_kernel and consumed by blend_kernel: 3 x float4 = 48 B.
+//   a = (cxp, cyp, A, B)   pixel-space centre, conic A and B (B carries the y-axis sign)
+//   b = (C, opacity, hx, hy) conic C, opacity, 3-sigma half extents in pixels
+//   c = (r, g, b, pth)     SH colour (unclamped), conservative power threshold below which
+//                          alpha < 1/255 is certain
+struct Rec {
+  float4 a, b, c;
+};
+
+// Frame status written by the device, copied to pinned host memory once per frame.
+struct FrameStatus {
+  unsigned long long n_instances;  // total (tile, Gaussian) pairs wanted
+  unsigned int n_visible;
+  unsigned int pad;
+};
+
+#define SPLAT_DEVINL __device__ __forceinline__
+
+}  // namespace splat

@@ -1,0 +1,233 @@
+// sort.cuh -- K3: stable LSD radix sort of (u32 key, u32 value) pairs, 8 bits per pass, plus
+// the exclusive scan it and the binning stage share.
+//
+// Replaces the reference's `indices.sort_by(|a,b| z[a].partial_cmp(&z[b]))`
+// (gaussians.rs:303, :314, :469 -- a stable merge sort on view-space z).  The frame's
+// (tile | depth) ordering is produced as an LSD radix sort whose four depth-digit passes run
+// on the N Gaussians *before* they are duplicated per tile (duplicates share the depth key,
+// so sorting them after duplication would move I >= N items through the same four passes),
+// and whose tile-digit passes run on the I tile instances.  Stability of every pass keeps
+// equal depths in ascending Gaussian index, exactly like the reference's stable sort.
+//
+// Per pass: histogram per 4096-key block -> exclusive scan over the (digit, block) table ->
+// scatter.  The scatter ranks keys with warp match-any (stable), reorders the block in shared
+// memory so that each digit's run is written with coalesced stores.
+// Algorithmic bytes per pass: 4 (hist read) + 8 (read) + 8 (write) = 20 B per pair.
+#pragma once
+#include "common.cuh"
+
+namespace splat {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_BLOCK = RS_THREADS * RS_ITEMS;   // 4096 pairs per CTA
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_WARP_SPAN = RS_ITEMS * 32;       // 512 consecutive pairs per warp
+
+SPLAT_DEVINL uint32_t rs_count(const uint32_t *n_ptr, uint32_t n_fixed) {
+  return n_ptr ? *n_ptr : n_fixed;
+}
+
+// hist[d * nblk + blk] = number of keys of block blk whose digit is d
+__global__ void __launch_bounds__(RS_THREADS)
+rs_hist_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ n_ptr, uint32_t n_fixed,
+               int shift, uint32_t *__restrict__ hist, uint32_t nblk) {
+  __shared__ uint32_t h[256];
+  const uint32_t n = rs_count(n_ptr, n_fixed);
+  const uint32_t base = blockIdx.x * RS_BLOCK;
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  if (base < n) {
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; ++k) {
+      const uint32_t idx = base + k * RS_THREADS + threadIdx.x;
+      if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & 0xFFu], 1u);
+    }
+  }
+  __syncthreads();
+  hist[threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                  uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
+                  const uint32_t *__restrict__ n_ptr, uint32_t n_fixed, int shift,
+                  const uint32_t *__restrict__ hist_scanned, uint32_t nblk) {
+  __shared__ uint32_t cnt[RS_WARPS][256];   // per-warp digit counts, then exclusive warp bases
+  __shared__ uint32_t dbase[256];           // block-local start of each digit's run
+  __shared__ uint32_t gofs[256];            // global offset of the run minus dbase
+  __shared__ uint32_t skey[RS_BLOCK];
+  __shared__ uint32_t sval[RS_BLOCK];
+  __shared__ uint32_t wsum[RS_WARPS];
+
+  const uint32_t n = rs_count(n_ptr, n_fixed);
+  const uint32_t base = blockIdx.x * RS_BLOCK;
+  if (base >= n) return;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+  const uint32_t nvalid = min((uint32_t)RS_BLOCK, n - base);
+  const uint32_t lt_mask = (1u << lane) - 1u;
+
+#pragma unroll
+  for (int q = 0; q < RS_WARPS; ++q) cnt[q][tid] = 0;
+  __syncthreads();
+
+  uint32_t key[RS_ITEMS], val[RS_ITEMS];
+  uint16_t rank[RS_ITEMS];
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    const uint32_t li = w * RS_WARP_SPAN + k * 32 + lane;   // index order == (warp, round, lane)
+    const bool valid = li < nvalid;
+    key[k] = valid ? keys_in[base + li] : 0xFFFFFFFFu;
+    val[k] = valid ? vals_in[base + li] : 0u;
+    const uint32_t d = (key[k] >> shift) & 0xFFu;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, valid ? d : 0x100u);
+    const int leader = __ffs(peers) - 1;
+    uint32_t old = 0;
+    if (valid && (int)lane == leader) {
+      old = cnt[w][d];
+      cnt[w][d] = old + __popc(peers);
+    }
+    old = __shfl_sync(0xFFFFFFFFu, old, leader);
+    rank[k] = (uint16_t)(old + __popc(peers & lt_mask));
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // digit tid: exclusive bases across warps + block total
+  uint32_t tot = 0;
+#pragma unroll
+  for (int q = 0; q < RS_WARPS; ++q) {
+    const uint32_t t = cnt[q][tid];
+    cnt[q][tid] = tot;
+    tot += t;
+  }
+  // exclusive scan of the 256 digit totals
+  uint32_t incl = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= (uint32_t)o) incl += t;
+  }
+  if (lane == 31) wsum[w] = incl;
+  __syncthreads();
+  uint32_t wbase = 0;
+#pragma unroll
+  for (int q = 0; q < RS_WARPS; ++q) wbase += (q < (int)w) ? wsum[q] : 0u;
+  const uint32_t excl = wbase + incl - tot;
+  dbase[tid] = excl;
+  gofs[tid] = hist_scanned[tid * nblk + blockIdx.x] - excl;
+  __syncthreads();
+
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    const uint32_t li = w * RS_WARP_SPAN + k * 32 + lane;
+    if (li < nvalid) {
+      const uint32_t d = (key[k] >> shift) & 0xFFu;
+      const uint32_t lp = dbase[d] + cnt[w][d] + rank[k];
+      skey[lp] = key[k];
+      sval[lp] = val[k];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    const uint32_t lp = k * RS_THREADS + tid;
+    if (lp < nvalid) {
+      const uint32_t kk = skey[lp];
+      const uint32_t g = gofs[(kk >> shift) & 0xFFu] + lp;
+      keys_out[g] = kk;
+      vals_out[g] = sval[lp];
+    }
+  }
+}
+
+// ---------------------------------------------------------------- exclusive scan (u32)
+constexpr int SC_THREADS = 256;
+constexpr int SC_ITEMS = 8;
+constexpr int SC_BLOCK = SC_THREADS * SC_ITEMS;   // 2048
+
+SPLAT_DEVINL uint32_t block_reduce_sum(uint32_t v, uint32_t *sh /* 8 */) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  uint32_t t = 0;
+#pragma unroll
+  for (int q = 0; q < SC_THREADS / 32; ++q) t += sh[q];
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(SC_THREADS)
+scan_reduce_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ partial, uint32_t n) {
+  __shared__ uint32_t sh[SC_THREADS / 32];
+  const uint32_t base = blockIdx.x * SC_BLOCK + threadIdx.x * SC_ITEMS;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < SC_ITEMS; ++k) s += (base + k < n) ? in[base + k] : 0u;
+  s = block_reduce_sum(s, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// single CTA: exclusive scan of the block partials (64-bit running sum for the grand total)
+__global__ void __launch_bounds__(1024)
+scan_partials_kernel(uint32_t *__restrict__ partial, uint32_t np, unsigned long long *total_out) {
+  __shared__ unsigned long long wsum[32];
+  __shared__ unsigned long long carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  for (uint32_t base = 0; base < np; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const unsigned long long v = (i < np) ? partial[i] : 0ull;
+    unsigned long long incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= (uint32_t)o) incl += t;
+    }
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    unsigned long long wb = 0;
+    for (uint32_t q = 0; q < w; ++q) wb += wsum[q];
+    const unsigned long long carry = carry_s;
+    if (i < np) partial[i] = (uint32_t)(carry + wb + incl - v);
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + wb + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = carry_s;
+}
+
+__global__ void __launch_bounds__(SC_THREADS)
+scan_apply_kernel(const uint32_t *in, uint32_t *out,   // in == out is allowed (in-place)
+                  const uint32_t *__restrict__ partial, uint32_t n) {
+  __shared__ uint32_t wsum[SC_THREADS / 32];
+  const uint32_t base = blockIdx.x * SC_BLOCK + threadIdx.x * SC_ITEMS;
+  uint32_t v[SC_ITEMS], s = 0;
+#pragma unroll
+  for (int k = 0; k < SC_ITEMS; ++k) {
+    v[k] = (base + k < n) ? in[base + k] : 0u;
+    s += v[k];
+  }
+  const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  uint32_t incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= (uint32_t)o) incl += t;
+  }
+  if (lane == 31) wsum[w] = incl;
+  __syncthreads();
+  uint32_t wb = 0;
+#pragma unroll
+  for (int q = 0; q < SC_THREADS / 32; ++q) wb += (q < (int)w) ? wsum[q] : 0u;
+  uint32_t run = partial[blockIdx.x] + wb + incl - s;
+#pragma unroll
+  for (int k = 0; k < SC_ITEMS; ++k) {
+    if (base + k < n) out[base + k] = run;
+    run += v[k];
+  }
+}
+
+}  // namespace splat

@@ -1,0 +1,506 @@
+// splat_api.cu -- the C ABI of include/splat.h: context, scene upload, frame orchestration.
+//
+// Frame = render_to_buffer (pipelines.rs:66-86 / :260-280):
+//   K1 project -> K3a depth radix sort (N keys) -> K2 tile count + scan -> [host reads the
+//   instance count] -> K2 emit -> K3b tile radix sort (I keys) -> K4 ranges -> K5 blend.
+// One host<->device round trip per frame (the instance count), everything else is enqueued
+// asynchronously on one stream; the framebuffer upload runs on a second stream and is only
+// waited for by the blend kernel.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/splat.h"
+#include "bin.cuh"
+#include "blend.cuh"
+#include "common.cuh"
+#include "project.cuh"
+#include "sort.cuh"
+
+using namespace splat;
+
+namespace {
+enum { EV_START = 0, EV_PROJECT, EV_DSORT, EV_COUNT, EV_EMIT, EV_TSORT, EV_RANGES, EV_BLEND,
+       EV_H2D0, EV_H2D1, EV_D2H0, EV_D2H1, EV_COUNT_ };
+}
+
+struct splat_ctx {
+  splat_config cfg{};
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev[EV_COUNT_] = {};
+  cudaEvent_t status_ev = nullptr, h2d_done = nullptr;
+  std::string err;
+
+  uint32_t n = 0;
+  float4 *scene = nullptr;
+  Rec *recs = nullptr;
+  uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
+  uint2 *rects = nullptr;
+  uint32_t *cnt = nullptr, *offs = nullptr;
+  uint32_t *hist = nullptr; size_t hist_cap = 0;
+  uint32_t *partial = nullptr; size_t partial_cap = 0;
+  uint64_t inst_cap = 0;
+  uint32_t *ikeys[2] = {nullptr, nullptr}, *ivals[2] = {nullptr, nullptr};
+  uint2 *ranges = nullptr; size_t ranges_cap = 0;
+  FrameStatus *d_status = nullptr, *h_status = nullptr;
+  uint32_t *d_fb = nullptr; size_t fb_cap = 0;
+
+  // last frame
+  int order_buf = 0;          // which vals[] holds the depth order
+  bool have_frame = false, host_copy = false;
+  uint32_t retried = 0;
+  uint64_t launches = 0, last_instances = 0, last_visible = 0, last_tiles = 0;
+};
+
+namespace {
+
+int fail(splat_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess) {
+  if (c) {
+    c->err = what;
+    if (e != cudaSuccess) { c->err += ": "; c->err += cudaGetErrorString(e); }
+  }
+  return code;
+}
+
+#define CU(expr)                                                              \
+  do {                                                                        \
+    cudaError_t e__ = (expr);                                                 \
+    if (e__ != cudaSuccess) return fail(c, e__ == cudaErrorMemoryAllocation ? SPLAT_ERR_NOMEM : SPLAT_ERR_CUDA, #expr, e__); \
+  } while (0)
+
+template <typename T>
+cudaError_t dev_alloc(T **p, size_t count) {
+  return cudaMalloc(reinterpret_cast<void **>(p), std::max<size_t>(count, 1) * sizeof(T));
+}
+template <typename T>
+void dev_free(T *&p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+// in-place exclusive scan of m u32 values; optional 64-bit grand total
+int scan_u32(splat_ctx *c, cudaStream_t s, uint32_t *data, uint32_t m, unsigned long long *total_out) {
+  const uint32_t np = std::max(1u, cdiv(m, SC_BLOCK));
+  scan_reduce_kernel<<<np, SC_THREADS, 0, s>>>(data, c->partial, m);
+  scan_partials_kernel<<<1, 1024, 0, s>>>(c->partial, np, total_out);
+  scan_apply_kernel<<<np, SC_THREADS, 0, s>>>(data, data, c->partial, m);
+  c->launches += 3;
+  return SPLAT_OK;
+}
+
+// stable LSD radix sort of (key, value) pairs on bits [0, bits); returns the buffer index
+// (0/1) that holds the result
+int radix_sort(splat_ctx *c, cudaStream_t s, uint32_t *keys[2], uint32_t *vals[2], uint32_t n, int bits) {
+  int cur = 0;
+  if (n == 0) return cur;
+  const uint32_t nblk = cdiv(n, RS_BLOCK);
+  for (int shift = 0; shift < bits; shift += 8) {
+    rs_hist_kernel<<<nblk, RS_THREADS, 0, s>>>(keys[cur], nullptr, n, shift, c->hist, nblk);
+    c->launches += 1;
+    scan_u32(c, s, c->hist, 256u * nblk, nullptr);
+    rs_scatter_kernel<<<nblk, RS_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1],
+                                                  nullptr, n, shift, c->hist, nblk);
+    c->launches += 1;
+    cur ^= 1;
+  }
+  return cur;
+}
+
+int ensure_scratch(splat_ctx *c, uint64_t sort_items) {
+  const size_t need_hist = 256ull * cdiv(sort_items, RS_BLOCK);
+  if (need_hist > c->hist_cap) {
+    dev_free(c->hist);
+    CU(dev_alloc(&c->hist, need_hist));
+    c->hist_cap = need_hist;
+  }
+  const size_t need_part = std::max<size_t>(cdiv(need_hist, SC_BLOCK), cdiv(c->n, SC_BLOCK)) + 1;
+  if (need_part > c->partial_cap) {
+    dev_free(c->partial);
+    CU(dev_alloc(&c->partial, need_part));
+    c->partial_cap = need_part;
+  }
+  return SPLAT_OK;
+}
+
+int ensure_instances(splat_ctx *c, uint64_t want) {
+  if (want <= c->inst_cap) return SPLAT_OK;
+  if (want >= 0xFFFFFFFFull) return fail(c, SPLAT_ERR_UNSUPPORTED, "more than 2^32-1 tile instances in one stripe");
+  uint64_t cap = std::min<uint64_t>(0xFFFFFFFEull, want + want / 4 + 4096);
+  for (int k = 0; k < 2; ++k) { dev_free(c->ikeys[k]); dev_free(c->ivals[k]); }
+  c->inst_cap = 0;
+  for (int k = 0; k < 2; ++k) {
+    CU(dev_alloc(&c->ikeys[k], cap));
+    CU(dev_alloc(&c->ivals[k], cap));
+  }
+  c->inst_cap = cap;
+  return ensure_scratch(c, std::max<uint64_t>(cap, c->n));
+}
+
+void free_scene(splat_ctx *c) {
+  dev_free(c->scene); dev_free(c->recs); dev_free(c->rects); dev_free(c->cnt); dev_free(c->offs);
+  for (int k = 0; k < 2; ++k) { dev_free(c->keys[k]); dev_free(c->vals[k]); }
+  c->n = 0;
+  c->have_frame = false;
+}
+
+int alloc_scene(splat_ctx *c, uint64_t n) {
+  if (n == 0 || n > 0x7FFFFFFFull) return fail(c, SPLAT_ERR_INVALID, "n must be in [1, 2^31)");
+  free_scene(c);
+  CU(dev_alloc(&c->scene, (size_t)SCENE_PLANES * n));
+  CU(dev_alloc(&c->recs, n));
+  CU(dev_alloc(&c->rects, n));
+  CU(dev_alloc(&c->cnt, n));
+  CU(dev_alloc(&c->offs, n));
+  for (int k = 0; k < 2; ++k) { CU(dev_alloc(&c->keys[k], n)); CU(dev_alloc(&c->vals[k], n)); }
+  c->n = (uint32_t)n;
+  int rc = ensure_scratch(c, n);
+  if (rc) return rc;
+  return ensure_instances(c, std::max<uint64_t>(c->cfg.max_instances, 1u << 20));
+}
+
+int make_params(splat_ctx *c, const splat_camera *cam, uint32_t W, uint32_t H, uint32_t row0,
+                uint32_t row1, FrameParams *P) {
+  if (!cam) return fail(c, SPLAT_ERR_INVALID, "camera is null");
+  if (W == 0 || H == 0 || W > 65535u * TILE || H > 65535u * TILE) return fail(c, SPLAT_ERR_INVALID, "bad target size");
+  if (!(cam->w == (float)W && cam->h == (float)H))
+    return fail(c, SPLAT_ERR_UNSUPPORTED, "camera.w/h must equal the target size");
+  if (row0 >= row1 || row1 > H || row0 % TILE != 0 || (row1 % TILE != 0 && row1 != H))
+    return fail(c, SPLAT_ERR_INVALID, "stripe [row0,row1) must be non-empty, inside the image and tile aligned");
+  std::memcpy(P->view, cam->view, sizeof(P->view));
+  std::memcpy(P->proj, cam->proj, sizeof(P->proj));
+  std::memcpy(P->cam_pos, cam->position, sizeof(P->cam_pos));
+  P->focal = cam->focal; P->htanx = cam->htanx; P->htany = cam->htany;
+  P->lowpass = c->cfg.lowpass;
+  P->sample_off = c->cfg.sample_offset;
+  P->ysign = c->cfg.y_down ? 1.0f : -1.0f;
+  P->zclip_mode = c->cfg.zclip_mode;
+  P->W = W; P->H = H; P->row0 = row0; P->row1 = row1;
+  P->tiles_x = cdiv(W, TILE);
+  P->tile_y0 = row0 / TILE;
+  P->tiles_y = cdiv(row1, TILE) - P->tile_y0;
+  P->n = c->n;
+  return SPLAT_OK;
+}
+
+int ilog2_ceil(uint32_t v) {
+  int b = 0;
+  while ((1ull << b) < v) ++b;
+  return std::max(b, 1);
+}
+
+// Enqueue one frame on `s`, writing rows [row0,row1) into fb_rows_dev.  If wait_ev is set the
+// blend kernel waits for it (framebuffer upload on the copy stream).
+int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cudaStream_t s, cudaEvent_t wait_ev) {
+  const uint32_t n = c->n;
+  c->launches = 0;
+  CU(cudaEventRecord(c->ev[EV_START], s));
+  CU(cudaMemsetAsync(c->d_status, 0, sizeof(FrameStatus), s));
+  project_kernel<<<cdiv(n, 256), 256, 0, s>>>(c->scene, P, c->recs, c->keys[0], c->vals[0], c->rects);
+  c->launches += 1;
+  CU(cudaEventRecord(c->ev[EV_PROJECT], s));
+  const int cur = radix_sort(c, s, c->keys, c->vals, n, 32);
+  c->order_buf = cur;
+  CU(cudaEventRecord(c->ev[EV_DSORT], s));
+  tile_count_kernel<<<cdiv(n, 256), 256, 0, s>>>(c->keys[cur], c->vals[cur], c->rects, c->cnt, n, c->d_status);
+  c->launches += 1;
+  // exclusive scan cnt -> offs, grand total -> status.n_instances
+  {
+    const uint32_t np = std::max(1u, cdiv(n, SC_BLOCK));
+    scan_reduce_kernel<<<np, SC_THREADS, 0, s>>>(c->cnt, c->partial, n);
+    scan_partials_kernel<<<1, 1024, 0, s>>>(c->partial, np, &c->d_status->n_instances);
+    scan_apply_kernel<<<np, SC_THREADS, 0, s>>>(c->cnt, c->offs, c->partial, n);
+    c->launches += 3;
+  }
+  CU(cudaEventRecord(c->ev[EV_COUNT], s));
+  CU(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(FrameStatus), cudaMemcpyDeviceToHost, s));
+  CU(cudaEventRecord(c->status_ev, s));
+  CU(cudaEventSynchronize(c->status_ev));   // the frame's only host round trip
+  const uint64_t I = c->h_status->n_instances;
+  c->last_instances = I;
+  c->last_visible = c->h_status->n_visible;
+  c->last_tiles = (uint64_t)P.tiles_x * P.tiles_y;
+  if (I > c->inst_cap) {
+    int rc = ensure_instances(c, I);
+    if (rc) return rc;
+    c->retried += 1;
+  }
+  const uint32_t T = P.tiles_x * P.tiles_y;
+  if (T > c->ranges_cap) {
+    dev_free(c->ranges);
+    CU(dev_alloc(&c->ranges, T));
+    c->ranges_cap = T;
+  }
+  int icur = 0;
+  if (I > 0) {
+    emit_instances_kernel<<<cdiv(n, 256), 256, 0, s>>>(c->vals[cur], c->rects, c->cnt, c->offs,
+                                                        c->ikeys[0], c->ivals[0], n, P.tiles_x);
+    c->launches += 1;
+  }
+  CU(cudaEventRecord(c->ev[EV_EMIT], s));
+  if (I > 0) icur = radix_sort(c, s, c->ikeys, c->ivals, (uint32_t)I, ilog2_ceil(T));
+  CU(cudaEventRecord(c->ev[EV_TSORT], s));
+  CU(cudaMemsetAsync(c->ranges, 0, (size_t)T * sizeof(uint2), s));
+  if (I > 0) {
+    tile_ranges_kernel<<<cdiv(I, 256), 256, 0, s>>>(c->ikeys[icur], (uint32_t)I, c->ranges);
+    c->launches += 1;
+  }
+  CU(cudaEventRecord(c->ev[EV_RANGES], s));
+  if (wait_ev) CU(cudaStreamWaitEvent(s, wait_ev, 0));
+  if (I > 0) {
+    blend_kernel<<<dim3(P.tiles_x, P.tiles_y), BL_THREADS, 0, s>>>(c->ranges, c->ivals[icur], c->recs, fb_rows_dev, P);
+    c->launches += 1;
+  }
+  CU(cudaEventRecord(c->ev[EV_BLEND], s));
+  CU(cudaGetLastError());
+  c->have_frame = true;
+  return SPLAT_OK;
+}
+
+int upload_common(splat_ctx *c, uint64_t n) {
+  CU(cudaSetDevice(c->cfg.device));
+  return alloc_scene(c, n);
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t splat_abi_version(void) { return SPLAT_ABI_VERSION; }
+
+void splat_config_default(splat_config *cfg) {
+  if (!cfg) return;
+  cfg->device = 0;
+  cfg->lowpass = 0.3f;        // Pipeline02 (gaussians.rs:517-518)
+  cfg->y_down = 1;
+  cfg->zclip_mode = 0;
+  cfg->sample_offset = 0.5f;
+  cfg->tile = TILE;
+  cfg->max_instances = 0;
+}
+
+int splat_create(splat_ctx **out, const splat_config *cfg) {
+  if (!out) return SPLAT_ERR_INVALID;
+  *out = nullptr;
+  splat_ctx *c = new (std::nothrow) splat_ctx();
+  if (!c) return SPLAT_ERR_NOMEM;
+  if (cfg) c->cfg = *cfg; else splat_config_default(&c->cfg);
+  auto bail = [&](int code) { splat_destroy(c); return code; };
+  if (c->cfg.tile != (uint32_t)TILE) return bail(SPLAT_ERR_UNSUPPORTED);
+  if (!(c->cfg.lowpass >= 0.0f) || !std::isfinite(c->cfg.sample_offset)) return bail(SPLAT_ERR_INVALID);
+  if (cudaSetDevice(c->cfg.device) != cudaSuccess) return bail(SPLAT_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(SPLAT_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(SPLAT_ERR_CUDA);
+  for (int i = 0; i < EV_COUNT_; ++i)
+    if (cudaEventCreate(&c->ev[i]) != cudaSuccess) return bail(SPLAT_ERR_CUDA);
+  if (cudaEventCreateWithFlags(&c->status_ev, cudaEventDisableTiming) != cudaSuccess) return bail(SPLAT_ERR_CUDA);
+  if (cudaEventCreateWithFlags(&c->h2d_done, cudaEventDisableTiming) != cudaSuccess) return bail(SPLAT_ERR_CUDA);
+  if (dev_alloc(&c->d_status, 1) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
+  if (cudaMallocHost(reinterpret_cast<void **>(&c->h_status), sizeof(FrameStatus)) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
+  *out = c;
+  return SPLAT_OK;
+}
+
+void splat_destroy(splat_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  free_scene(c);
+  dev_free(c->hist); dev_free(c->partial); dev_free(c->ranges); dev_free(c->d_status); dev_free(c->d_fb);
+  for (int k = 0; k < 2; ++k) { dev_free(c->ikeys[k]); dev_free(c->ivals[k]); }
+  if (c->h_status) cudaFreeHost(c->h_status);
+  for (int i = 0; i < EV_COUNT_; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->status_ev) cudaEventDestroy(c->status_ev);
+  if (c->h2d_done) cudaEventDestroy(c->h2d_done);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  delete c;
+}
+
+const char *splat_last_error(const splat_ctx *c) { return c ? c->err.c_str() : "null context"; }
+
+int splat_upload_soa(splat_ctx *c, const float *pos4, const float *scale3, const float *opacity,
+                     const float *rot_xyzw, const float *sh48, uint64_t n) {
+  if (!c) return SPLAT_ERR_INVALID;
+  if (!pos4 || !scale3 || !opacity || !rot_xyzw || !sh48) return fail(c, SPLAT_ERR_INVALID, "null scene array");
+  int rc = upload_common(c, n);
+  if (rc) return rc;
+  float *raw = nullptr;   // staging: pos4 | rot | scale3 | opacity | sh48
+  const size_t total = (size_t)n * (4 + 4 + 3 + 1 + 48);
+  CU(dev_alloc(&raw, total));
+  float *d_pos = raw, *d_rot = raw + 4 * n, *d_scale = raw + 8 * n, *d_op = raw + 11 * n, *d_sh = raw + 12 * n;
+  cudaError_t e = cudaMemcpyAsync(d_pos, pos4, n * 16, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_rot, rot_xyzw, n * 16, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_scale, scale3, n * 12, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_op, opacity, n * 4, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_sh, sh48, n * 192, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) {
+    pack_scene_kernel<<<cdiv(n, 256), 256, 0, c->stream>>>(reinterpret_cast<const float4 *>(d_pos), d_scale, d_op,
+                                                           reinterpret_cast<const float4 *>(d_rot), d_sh, c->scene, (uint32_t)n);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(raw);
+  if (e != cudaSuccess) { free_scene(c); return fail(c, SPLAT_ERR_CUDA, "scene upload", e); }
+  return SPLAT_OK;
+}
+
+int splat_upload_aos(splat_ctx *c, const float *g59, uint64_t n) {
+  if (!c) return SPLAT_ERR_INVALID;
+  if (!g59) return fail(c, SPLAT_ERR_INVALID, "null scene array");
+  int rc = upload_common(c, n);
+  if (rc) return rc;
+  float *raw = nullptr;
+  CU(dev_alloc(&raw, (size_t)n * 59));
+  cudaError_t e = cudaMemcpyAsync(raw, g59, n * 59 * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) {
+    pack_scene_aos_kernel<<<cdiv(n, 256), 256, 0, c->stream>>>(raw, c->scene, (uint32_t)n);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(raw);
+  if (e != cudaSuccess) { free_scene(c); return fail(c, SPLAT_ERR_CUDA, "scene upload", e); }
+  return SPLAT_OK;
+}
+
+int splat_render_device(splat_ctx *c, const splat_camera *cam, void *fb_rows_dev, uint32_t W, uint32_t H,
+                        uint32_t row0, uint32_t row1, void *stream) {
+  if (!c) return SPLAT_ERR_INVALID;
+  if (!c->n) return fail(c, SPLAT_ERR_STATE, "no scene uploaded");
+  if (!fb_rows_dev) return fail(c, SPLAT_ERR_INVALID, "framebuffer is null");
+  FrameParams P;
+  int rc = make_params(c, cam, W, H, row0, row1, &P);
+  if (rc) return rc;
+  CU(cudaSetDevice(c->cfg.device));
+  c->host_copy = false;
+  return render_frame(c, P, static_cast<uint32_t *>(fb_rows_dev), stream ? static_cast<cudaStream_t>(stream) : c->stream, nullptr);
+}
+
+int splat_render_rows(splat_ctx *c, const splat_camera *cam, uint32_t *fb_rows, uint32_t W, uint32_t H,
+                      uint32_t row0, uint32_t row1) {
+  if (!c) return SPLAT_ERR_INVALID;
+  if (!c->n) return fail(c, SPLAT_ERR_STATE, "no scene uploaded");
+  if (!fb_rows) return fail(c, SPLAT_ERR_INVALID, "framebuffer is null");
+  FrameParams P;
+  int rc = make_params(c, cam, W, H, row0, row1, &P);
+  if (rc) return rc;
+  CU(cudaSetDevice(c->cfg.device));
+  const size_t px = (size_t)(row1 - row0) * W;
+  if (px > c->fb_cap) {
+    CU(cudaStreamSynchronize(c->stream));
+    dev_free(c->d_fb);
+    CU(dev_alloc(&c->d_fb, px));
+    c->fb_cap = px;
+  }
+  // upload on the copy stream: overlaps project/sort/binning, only blend waits for it
+  CU(cudaEventRecord(c->ev[EV_H2D0], c->copy_stream));
+  CU(cudaMemcpyAsync(c->d_fb, fb_rows, px * 4, cudaMemcpyHostToDevice, c->copy_stream));
+  CU(cudaEventRecord(c->ev[EV_H2D1], c->copy_stream));
+  CU(cudaEventRecord(c->h2d_done, c->copy_stream));
+  rc = render_frame(c, P, c->d_fb, c->stream, c->h2d_done);
+  if (rc) { cudaStreamSynchronize(c->copy_stream); return rc; }
+  CU(cudaEventRecord(c->ev[EV_D2H0], c->stream));
+  CU(cudaMemcpyAsync(fb_rows, c->d_fb, px * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaEventRecord(c->ev[EV_D2H1], c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->host_copy = true;
+  return SPLAT_OK;
+}
+
+int splat_render(splat_ctx *c, const splat_camera *cam, uint32_t *fb, uint32_t W, uint32_t H) {
+  return splat_render_rows(c, cam, fb, W, H, 0, H);
+}
+
+int splat_get_timings(splat_ctx *c, splat_timings *t) {
+  if (!c || !t) return SPLAT_ERR_INVALID;
+  if (!c->have_frame) return fail(c, SPLAT_ERR_STATE, "no frame rendered yet");
+  CU(cudaSetDevice(c->cfg.device));
+  CU(cudaEventSynchronize(c->ev[EV_BLEND]));
+  std::memset(t, 0, sizeof(*t));
+  auto el = [&](int a, int b) { float ms = 0.f; cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]); return ms; };
+  t->project_ms = el(EV_START, EV_PROJECT);
+  t->sort_ms = el(EV_PROJECT, EV_DSORT) + el(EV_EMIT, EV_TSORT);
+  t->bin_ms = el(EV_DSORT, EV_COUNT) + el(EV_COUNT, EV_EMIT) + el(EV_TSORT, EV_RANGES);
+  t->blend_ms = el(EV_RANGES, EV_BLEND);
+  t->total_ms = el(EV_START, EV_BLEND);
+  if (c->host_copy) {
+    CU(cudaEventSynchronize(c->ev[EV_D2H1]));
+    t->h2d_ms = el(EV_H2D0, EV_H2D1);
+    t->d2h_ms = el(EV_D2H0, EV_D2H1);
+  }
+  t->frames_retried = c->retried;
+  t->n_gaussians = c->n;
+  t->n_visible = c->last_visible;
+  t->n_instances = c->last_instances;
+  t->n_tiles = c->last_tiles;
+  t->kernel_launches = c->launches;
+  return SPLAT_OK;
+}
+
+int splat_debug_project(splat_ctx *c, const splat_camera *cam, uint32_t W, uint32_t H, float *records12,
+                        uint32_t *depth_keys, uint32_t *tile_rects4) {
+  if (!c) return SPLAT_ERR_INVALID;
+  if (!c->n) return fail(c, SPLAT_ERR_STATE, "no scene uploaded");
+  FrameParams P;
+  int rc = make_params(c, cam, W, H, 0, H, &P);
+  if (rc) return rc;
+  CU(cudaSetDevice(c->cfg.device));
+  CU(cudaMemsetAsync(c->recs, 0, (size_t)c->n * sizeof(Rec), c->stream));
+  project_kernel<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->scene, P, c->recs, c->keys[0], c->vals[0], c->rects);
+  CU(cudaGetLastError());
+  if (records12) CU(cudaMemcpyAsync(records12, c->recs, (size_t)c->n * sizeof(Rec), cudaMemcpyDeviceToHost, c->stream));
+  if (depth_keys) CU(cudaMemcpyAsync(depth_keys, c->keys[0], (size_t)c->n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (tile_rects4) CU(cudaMemcpyAsync(tile_rects4, c->rects, (size_t)c->n * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->have_frame = false;
+  return SPLAT_OK;
+}
+
+int splat_debug_read_order(splat_ctx *c, uint32_t *order, uint64_t cap, uint64_t *n_visible) {
+  if (!c || !order || !n_visible) return SPLAT_ERR_INVALID;
+  if (!c->have_frame) return fail(c, SPLAT_ERR_STATE, "no frame rendered yet");
+  CU(cudaSetDevice(c->cfg.device));
+  CU(cudaDeviceSynchronize());
+  const uint64_t m = std::min<uint64_t>(cap, c->last_visible);
+  CU(cudaMemcpy(order, c->vals[c->order_buf], m * 4, cudaMemcpyDeviceToHost));
+  *n_visible = c->last_visible;
+  return SPLAT_OK;
+}
+
+int splat_debug_sort_pairs(splat_ctx *c, uint32_t *keys, uint32_t *vals, uint64_t n, int bits) {
+  // standalone exercise of the radix sort (tests): sorts host arrays in place
+  if (!c || !keys || !vals || n == 0 || n >= 0xFFFFFFFFull || bits < 1 || bits > 32) return SPLAT_ERR_INVALID;
+  CU(cudaSetDevice(c->cfg.device));
+  uint32_t *k[2] = {nullptr, nullptr}, *v[2] = {nullptr, nullptr};
+  int rc = SPLAT_OK;
+  const uint32_t saved_n = c->n;
+  for (int i = 0; i < 2; ++i) {
+    if (dev_alloc(&k[i], n) != cudaSuccess || dev_alloc(&v[i], n) != cudaSuccess) rc = SPLAT_ERR_NOMEM;
+  }
+  if (!rc) rc = ensure_scratch(c, n);
+  if (!rc) {
+    cudaMemcpy(k[0], keys, n * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(v[0], vals, n * 4, cudaMemcpyHostToDevice);
+    const int cur = radix_sort(c, c->stream, k, v, (uint32_t)n, bits);
+    cudaStreamSynchronize(c->stream);
+    cudaMemcpy(keys, k[cur], n * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(vals, v[cur], n * 4, cudaMemcpyDeviceToHost);
+    if (cudaGetLastError() != cudaSuccess) rc = fail(c, SPLAT_ERR_CUDA, "debug sort");
+  }
+  for (int i = 0; i < 2; ++i) { dev_free(k[i]); dev_free(v[i]); }
+  c->n = saved_n;
+  return rc;
+}
+
+int splat_pin_host(void *p, uint64_t bytes) {
+  return cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess ? SPLAT_OK : SPLAT_ERR_CUDA;
+}
+int splat_unpin_host(void *p) { return cudaHostUnregister(p) == cudaSuccess ? SPLAT_OK : SPLAT_ERR_CUDA; }
+
+}  // extern "C"

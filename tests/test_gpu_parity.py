@@ -1,0 +1,228 @@
+"""GPU parity tests: the CUDA path, driven through the C ABI (ctypes over libsplat_b200.so),
+against the CPU oracle on the same seeded inputs.  Integer / byte results (depth order,
+framebuffer pixels) must be bit-exact; per-Gaussian f32 records must be value-identical."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from splat_b200 import _lib
+
+    _lib.load()
+    return _lib
+
+
+def _camera(W, H, pos, yaw=0.0, pitch=0.0):
+    from splat_b200.camera import Camera
+
+    cam = Camera(H, W, pos)
+    cam.update_yaw_angle(yaw)
+    cam.update_pitch_angle(pitch)
+    cam.update_camera_pose()
+    return cam
+
+
+def _scene(n, seed, log_scale_mean=-4.0):
+    from splat_b200.gaussians import synthetic_scene
+
+    return synthetic_scene(n, seed=seed, log_scale_mean=log_scale_mean)
+
+
+DEMO_CAM = (-0.57651054, 2.99040512, -0.03924271)   # 02_ply_demo.rs:22
+
+
+def _render_both(lib, orc, scene, cam, W, H, lowpass=0.3, y_down=1, zclip_mode=0, fb0=None, rows=None):
+    ctx = lib.Context(device=0, lowpass=lowpass, y_down=y_down, zclip_mode=zclip_mode)
+    ctx.upload(scene)
+    fb = np.zeros((H, W), np.uint32) if fb0 is None else fb0.copy()
+    ref = fb.copy()
+    if rows is None:
+        ctx.render(lib.camera_struct(cam), fb)
+    else:
+        for r0, r1 in rows:
+            part = np.ascontiguousarray(fb[r0:r1])
+            ctx.render(lib.camera_struct(cam), part, r0, r1)
+            fb[r0:r1] = part
+    t = ctx.timings()
+    cfg = orc.make_config(lowpass=lowpass, y_down=y_down, zclip_mode=zclip_mode)
+    st = orc.render(scene, orc.camera_from(cam), cfg, ref)
+    ctx.close()
+    return fb, ref, t, st
+
+
+def test_radix_sort_matches_stable_argsort(lib):
+    ctx = lib.Context(device=0)
+    rng = np.random.default_rng(7)
+    for n, bits in [(1, 32), (31, 32), (4096, 32), (4097, 32), (100_003, 32), (1_000_000, 13), (300_000, 7)]:
+        keys = rng.integers(0, 2 ** bits, size=n, dtype=np.uint64).astype(np.uint32)
+        if n > 1000:   # many duplicates to exercise stability
+            keys[rng.integers(0, n, n // 2)] = keys[0]
+        vals = np.arange(n, dtype=np.uint32)
+        k2, v2 = keys.copy(), vals.copy()
+        ctx.debug_sort_pairs(k2, v2, bits)
+        order = np.argsort(keys, kind="stable")
+        assert np.array_equal(k2, keys[order])
+        assert np.array_equal(v2, order.astype(np.uint32))
+    ctx.close()
+
+
+@pytest.mark.parametrize("campos,W,H", [((0.0, 0.0, 5.0), 800, 600), (DEMO_CAM, 1280, 720)])
+def test_projection_records_match_oracle(lib, orc, campos, W, H):
+    """K1 vs orc_project: every float of the splat record, the culling decision and the depth
+    order key."""
+    scene = _scene(20_000, 0x5EED0010)
+    cam = _camera(W, H, campos, yaw=0.3)
+    ctx = lib.Context(device=0, lowpass=0.3)
+    ctx.upload(scene)
+    rec, keys, rects = ctx.debug_project(lib.camera_struct(cam))
+    sp = orc.project(scene, orc.camera_from(cam), orc.make_config(lowpass=0.3), W, H)
+    vis = sp["visible"] != 0
+    assert np.array_equal(keys != 0xFFFFFFFF, vis)
+    assert vis.sum() > 1000
+    want = np.stack([sp["cxp"], sp["cyp"], sp["conic"][:, 0], sp["conic_b_px"], sp["conic"][:, 2],
+                     sp["opacity"], sp["bbox"][:, 0], sp["bbox"][:, 1], sp["color"][:, 0],
+                     sp["color"][:, 1], sp["color"][:, 2]], axis=1)
+    got = rec[:, :11]
+    assert np.array_equal(got[vis], want[vis])   # value-identical f32 (== treats -0 and +0 alike)
+    # depth keys order exactly like z_view
+    z = sp["z_view"][vis]
+    k = keys[vis].astype(np.int64)
+    o = np.argsort(z, kind="stable")
+    assert np.all(np.diff(k[o]) >= 0)
+    assert np.array_equal(np.diff(k[o]) == 0, np.diff(z[o]) == 0)
+    ctx.close()
+
+
+def test_depth_order_matches_stable_sort(lib, orc):
+    scene = _scene(50_000, 0x5EED0011)
+    # force depth ties: duplicate positions
+    scene.positions[1000:2000] = scene.positions[0:1000]
+    cam = _camera(640, 480, (0.0, 0.0, 5.0))
+    ctx = lib.Context(device=0)
+    ctx.upload(scene)
+    fb = np.zeros((480, 640), np.uint32)
+    ctx.render(lib.camera_struct(cam), fb)
+    got = ctx.debug_order()
+    sp = orc.project(scene, orc.camera_from(cam), orc.make_config(), 640, 480)
+    want = orc.sort_visible(sp)
+    assert np.array_equal(got, want)
+    ctx.close()
+
+
+CASES = [
+    # name, n, seed, W, H, camera position, yaw, lowpass, log_scale_mean
+    ("c1_1k_256", 1_000, 0x5EED0001, 256, 256, (0.0, 0.0, 5.0), 0.0, 0.01, -4.0),
+    ("ragged_250x130", 3_000, 0x5EED0021, 250, 130, (0.0, 0.0, 4.0), 0.5, 0.3, -3.0),
+    ("big_splats", 500, 0x5EED0022, 640, 360, (0.0, 0.0, 3.0), 0.0, 0.3, -1.5),
+    ("inside_cloud", 30_000, 0x5EED0023, 800, 600, (0.5, 0.2, 0.4), 1.0, 0.3, -4.0),
+    ("demo_cam_100k", 100_000, 0x5EED0024, 1280, 720, DEMO_CAM, 0.0, 0.3, -4.0),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_framebuffer_bit_exact(lib, orc, case):
+    name, n, seed, W, H, pos, yaw, lowpass, lsm = case
+    scene = _scene(n, seed, lsm)
+    cam = _camera(W, H, pos, yaw=yaw)
+    fb, ref, t, st = _render_both(lib, orc, scene, cam, W, H, lowpass=lowpass)
+    assert st.pairs_in_rect > 0 and np.count_nonzero(ref) > 0
+    assert t["n_visible"] == st.n_visible
+    assert np.array_equal(fb, ref), f"{np.count_nonzero(fb != ref)} of {W*H} pixels differ"
+
+
+def test_blends_onto_existing_contents(lib, orc):
+    """render_to_buffer blends onto whatever the buffer holds (pipelines.rs:147-168 decode the
+    old pixel); untouched pixels keep their value including the alpha byte."""
+    W, H = 320, 200
+    rng = np.random.default_rng(3)
+    fb0 = rng.integers(0, 2 ** 32, size=(H, W), dtype=np.uint64).astype(np.uint32)
+    scene = _scene(800, 0x5EED0030, -3.0)
+    cam = _camera(W, H, (0.0, 0.0, 5.0))
+    fb, ref, _, _ = _render_both(lib, orc, scene, cam, W, H, fb0=fb0)
+    assert np.array_equal(fb, ref)
+    assert np.count_nonzero(fb == fb0) > 0 and np.count_nonzero(fb != fb0) > 0
+
+
+@pytest.mark.parametrize("y_down,zclip", [(0, 0), (1, 1), (0, 2)])
+def test_euc_switches(lib, orc, y_down, zclip):
+    W, H = 400, 300
+    scene = _scene(5_000, 0x5EED0031, -3.5)
+    cam = _camera(W, H, (0.3, -0.2, 2.0), yaw=0.2)
+    fb, ref, _, _ = _render_both(lib, orc, scene, cam, W, H, y_down=y_down, zclip_mode=zclip)
+    assert np.array_equal(fb, ref)
+
+
+def test_stripes_equal_full_frame(lib, orc):
+    """Multi-GPU sharding renders tile-row stripes independently; the union must be
+    byte-identical to the single full-frame render (per-pixel lists do not depend on the
+    partition)."""
+    W, H = 500, 330
+    scene = _scene(20_000, 0x5EED0032, -3.5)
+    cam = _camera(W, H, (0.0, 0.0, 4.0), yaw=0.4)
+    full, ref, _, _ = _render_both(lib, orc, scene, cam, W, H)
+    assert np.array_equal(full, ref)
+    for rows in ([(0, 160), (160, 330)], [(0, 96), (96, 192), (192, 288), (288, 330)]):
+        parts, _, _, _ = _render_both(lib, orc, scene, cam, W, H, rows=rows)
+        assert np.array_equal(parts, full)
+
+
+def test_degenerate_inputs_are_skipped(lib, orc):
+    """NaN / inf / zero-quaternion / behind-camera Gaussians: culled identically, never a crash."""
+    W, H = 256, 256
+    scene = _scene(2_000, 0x5EED0033, -3.0)
+    scene.positions[0, 0] = np.nan
+    scene.positions[1, 2] = np.inf
+    scene.rotations[2] = 0.0
+    scene.scales[3] = 0.0
+    scene.opacities[4] = np.nan
+    scene.opacities[5] = -1.0
+    scene.opacities[6] = 5.0
+    scene.sh[7, 0] = np.inf
+    scene.positions[8, :3] = (0.0, 0.0, 9.0)     # behind the camera
+    scene.positions[9, :3] = (0.0, 0.0, 4.999)   # closer than the near clip
+    scene.scales[10] = 1e-30
+    scene.scales[11] = 50.0
+    cam = _camera(W, H, (0.0, 0.0, 5.0))
+    fb, ref, t, st = _render_both(lib, orc, scene, cam, W, H)
+    assert t["n_visible"] == st.n_visible
+    assert np.array_equal(fb, ref)
+
+
+def test_pipeline_mirrors(lib, orc):
+    """The reference-shaped entry points: Pipeline01 (AoS, low-pass 0.01) and Pipeline02 (SoA, 0.3)
+    on the reference's own 4-Gaussian scene and 01_naive_gaussian.rs-like setup."""
+    from splat_b200.gaussians import GaussianList, naive_gaussians
+    from splat_b200.pipelines import GaussianSplatPipeline01, GaussianSplatPipeline02
+
+    W, H = 1280, 720
+    cam = _camera(W, H, (0.0, 0.0, 3.0))
+    for cls, gaussians, lowpass in [(GaussianSplatPipeline01, naive_gaussians(), 0.01),
+                                    (GaussianSplatPipeline02, GaussianList.naive_gaussians(), 0.3)]:
+        pipe = cls(gaussians, cam)
+        color = np.zeros((H, W), np.uint32)
+        pipe.render_to_buffer(color)
+        ref = np.zeros((H, W), np.uint32)
+        orc.render(GaussianList.naive_gaussians(), orc.camera_from(cam), orc.make_config(lowpass=lowpass), ref)
+        assert np.count_nonzero(ref) > 1000
+        assert np.array_equal(color, ref)
+
+
+def test_errors_not_crashes(lib):
+    ctx = lib.Context(device=0)
+    cam = _camera(64, 64, (0, 0, 5))
+    fb = np.zeros((64, 64), np.uint32)
+    with pytest.raises(lib.SplatError) as e:
+        ctx.render(lib.camera_struct(cam), fb)          # render before upload
+    assert e.value.code == -5
+    ctx.upload(_scene(10, 1))
+    cam2 = _camera(32, 64, (0, 0, 5))                  # camera.w/h != target
+    with pytest.raises(lib.SplatError) as e:
+        ctx._check(ctx.L.splat_render(ctx.h, lib.camera_struct(cam2), fb.ctypes.data, 64, 64))
+    assert e.value.code == -4
+    with pytest.raises(lib.SplatError) as e:
+        ctx._check(ctx.L.splat_render_rows(ctx.h, lib.camera_struct(cam), fb.ctypes.data, 64, 64, 8, 64))
+    assert e.value.code == -1                           # stripe not tile aligned
+    ctx.close()
