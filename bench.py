@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of the render hot path (BASELINE.json metric) on N B200s.
+
+  python bench.py --gpus 1 --steps K --warmup W            our arm
+  python bench.py --impl reference --steps K --warmup W    CPU restatement of the reference
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): C3 of SURVEY 8d -- a bicycle-sized synthetic scene, 6.1M
+Gaussians, 1920x1080, camera (0,0,5) orbiting 10 degrees of yaw per frame (main.rs:53-60),
+Pipeline02 semantics (low-pass 0.3).  A step = one frame: clear the framebuffer (main.rs:73)
+and render_to_buffer.
+
+  value  = frames/s with the framebuffer resident in HBM (splat_render_device), CUDA events.
+  e2e    = frames/s through the host-buffer C-ABI call the Rust shim makes (splat_render):
+           pinned host framebuffer -> H2D -> kernels -> D2H, wall clock around the call.
+  N > 1  = screen-tile stripes, one per rank, each rendered straight into that rank's slice of
+           a full-frame device buffer and gathered to rank 0 with NCCL send/recv.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 0x5EED0003
+LOWPASS = 0.3
+YAW_STEP = 10.0 * np.pi / 180.0
+TILE = 16
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2])); pw.append(float(p[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[5:9]):
+                if v.lower() == "active":
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_scene(n):
+    from splat_b200.gaussians import synthetic_scene
+    t = time.time()
+    sc = synthetic_scene(n, seed=SEED)
+    log(f"[bench] synthetic scene: {n} Gaussians in {time.time() - t:.1f}s")
+    return sc
+
+
+def orbit_cameras(W, H, count):
+    """camera structs for `count` consecutive frames, +10 degrees of yaw per frame"""
+    from splat_b200.camera import Camera
+    cam = Camera(H, W, (0.0, 0.0, 5.0))
+    out = []
+    for _ in range(count):
+        cam.update_yaw_angle(YAW_STEP)
+        cam.update_camera_pose()
+        out.append((cam.get_view_matrix().copy(), cam.get_project_matrix().copy(), cam.position.copy(),
+                    cam.get_htanfovxy_focal().copy(), float(cam.w), float(cam.h)))
+    return out
+
+
+class _CamView:
+    def __init__(self, t):
+        self.v, self.p, self.position, self.hf, self.w, self.h = t
+    def get_view_matrix(self): return self.v
+    def get_project_matrix(self): return self.p
+    def get_htanfovxy_focal(self): return self.hf
+
+
+def stripe_bounds(H, world):
+    """tile-row stripes, equal numbers of tile rows (remainder to the first ranks)"""
+    trows = (H + TILE - 1) // TILE
+    base, rem = divmod(trows, world)
+    bounds, r = [], 0
+    for k in range(world):
+        t = base + (1 if k < rem else 0)
+        bounds.append((min(r * TILE, H), min((r + t) * TILE, H)))
+        r += t
+    return bounds
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_frame_time(orc, scene, cov3d, camt, W, H, row_step, nthreads):
+    """One frame of the CPU restatement: project + stable sort over the whole scene, then the
+    quad rasteriser on every `row_step`-th 16-row tile stripe, scaled to the full frame."""
+    cam = orc.camera_from(_CamView(camt))
+    cfg = orc.make_config(lowpass=LOWPASS, nthreads=nthreads)
+    t0 = time.perf_counter()
+    sp = orc.project(scene, cam, cfg, W, H, cov3d=cov3d)
+    t1 = time.perf_counter()
+    order = orc.sort_visible(sp)
+    t2 = time.perf_counter()
+    trows = (H + TILE - 1) // TILE
+    rows = np.concatenate([np.arange(t * TILE, min((t + 1) * TILE, H)) for t in range(0, trows, row_step)])
+    fb = np.zeros((H, W), np.uint32)
+    st = orc.rasterize_rows(sp, order, cfg, fb, rows)
+    t3 = time.perf_counter()
+    scale = H / len(rows)
+    return {"project_s": t1 - t0, "sort_s": t2 - t1, "raster_sample_s": t3 - t2, "scale": scale,
+            "frame_s": (t1 - t0) + (t2 - t1) + (t3 - t2) * scale,
+            "pairs_in_rect_est": st.pairs_in_rect * scale, "rows_sampled": int(len(rows))}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path.  The Rust crate cannot be built here (no
+    cargo/rustc; euc is an un-vendored git dependency), so this times the C restatement of it
+    (oracle/, kind "port") with every host thread on the same scene, cameras and metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle as orc
+    orc.build()
+    W, H, n = args.width, args.height, args.n
+    cores = os.cpu_count() or 1
+    scene = make_scene(n)
+    cov3d = orc.compute_cov3d(scene.rotations, scene.scales)   # once per scene, like main.rs:24-26
+    cams = orbit_cameras(W, H, args.warmup + args.steps)
+    row_step = args.cpu_row_step or 16
+    times, last = [], None
+    for i, camt in enumerate(cams):
+        last = cpu_frame_time(orc, scene, cov3d, camt, W, H, row_step, cores)
+        if i >= args.warmup:
+            times.append(last["frame_s"])
+        log(f"[reference] frame {i}: {last['frame_s']:.2f}s est. (project {last['project_s']:.2f} sort {last['sort_s']:.2f} "
+            f"raster sample {last['raster_sample_s']:.2f} x{last['scale']:.1f})")
+    fps = len(times) / sum(times)
+    sample = (f"per step: project+stable sort of all {n} Gaussians, quad rasteriser on every {row_step}th 16-row "
+              f"tile stripe ({last['rows_sampled']} of {H} rows), raster time scaled x{last['scale']:.2f}")
+    line = {"impl": "reference", "metric": "frames/sec at 1080p (6M Gaussians)", "value": fps, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / fps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, world):
+    return {"workload": f"C3 bicycle-sized synthetic scene: {args.n} Gaussians (seed 0x{SEED:X}), "
+                        f"{args.width}x{args.height}, camera (0,0,5) orbiting 10 deg yaw/frame, Pipeline02 (low-pass 0.3)",
+            "n_gaussians": args.n, "width": args.width, "height": args.height,
+            "parallelism": f"screen-tile stripes x{world}" if world > 1 else "single GPU",
+            "l2_policy": "inputs larger than L2 (scene 160 B x N, per-frame buffers > 126 MB); no explicit flush"}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from splat_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        log(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()   # raises if libsplat_b200.so is missing: no CPU fallback
+
+    W, H, n = args.width, args.height, args.n
+    K, Wm = args.steps, args.warmup
+
+    # ---- scene: generated on rank 0, broadcast once over NCCL (C0), uploaded on every rank
+    shapes = [(n, 4), (n, 3), (n,), (n, 4), (n, 48)]
+    if rank == 0:
+        sc = make_scene(n)
+        host = [sc.positions, sc.scales, sc.opacities, sc.rotations, sc.sh]
+    if world > 1:
+        arrs = []
+        for i, shp in enumerate(shapes):
+            t = torch.from_numpy(host[i]).to(dev) if rank == 0 else torch.empty(shp, dtype=torch.float32, device=dev)
+            dist.broadcast(t, 0)
+            arrs.append(t.cpu().numpy())
+            del t
+        from splat_b200.gaussians import GaussianList
+        sc = GaussianList(*arrs)
+        torch.cuda.empty_cache()
+    ctx = _lib.Context(device=local, lowpass=LOWPASS)
+    t0 = time.time()
+    ctx.upload(sc)
+    log(f"[bench] rank {rank}: scene uploaded in {time.time() - t0:.1f}s")
+
+    bounds = stripe_bounds(H, world)
+    r0, r1 = bounds[rank]
+    cams_all = orbit_cameras(W, H, 2 * (Wm + K))
+    cam_structs = [_lib.camera_struct(_CamView(c)) for c in cams_all]
+
+    fb_dev = torch.zeros((H, W), dtype=torch.int32, device=dev)   # full frame; this rank owns rows r0:r1
+    stream = torch.cuda.current_stream()
+
+    def gather_frame():
+        """C1: stripes -> rank 0's full frame, straight from/into the render target (no staging)."""
+        if world == 1:
+            return
+        if rank == 0:
+            ops = [dist.P2POp(dist.irecv, fb_dev[b0:b1], k) for k, (b0, b1) in enumerate(bounds) if k != 0 and b1 > b0]
+        else:
+            ops = [dist.P2POp(dist.isend, fb_dev[r0:r1], 0)] if r1 > r0 else []
+        if ops:
+            for w_ in dist.batch_isend_irecv(ops):
+                w_.wait()
+
+    def frame_device(i):
+        if r1 > r0:
+            fb_dev[r0:r1].zero_()                      # main.rs:73 clear
+            ctx.render_device(cam_structs[i], fb_dev[r0:r1].data_ptr(), W, H, r0, r1, stream.cuda_stream)
+        gather_frame()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- value: device-resident frames
+    for i in range(Wm):
+        frame_device(i)
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage = {"project_ms": 0.0, "sort_ms": 0.0, "bin_ms": 0.0, "blend_ms": 0.0, "total_ms": 0.0}
+    inst_sum, launches = 0, 0
+    ev0.record(stream)
+    for i in range(Wm, Wm + K):
+        frame_device(i)
+        if r1 > r0:
+            tm = ctx.timings()                          # this frame's per-stage CUDA events
+            for k_ in stage:
+                stage[k_] += tm[k_]
+            inst_sum += tm["n_instances"]
+            launches += tm["kernel_launches"] + 1       # + the clear
+    ev1.record(stream)
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    lsum = torch.tensor([launches], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lsum, op=dist.ReduceOp.SUM)
+    ms_per_step = float(ms.item()) / K
+    value = 1000.0 / ms_per_step
+
+    # ---- e2e: the host-buffer call
+    host_fb = torch.zeros((H, W), dtype=torch.int32).pin_memory()
+    host_np = host_fb.numpy().view(np.uint32)
+    my_host = torch.zeros((max(r1 - r0, 1), W), dtype=torch.int32).pin_memory()
+
+    def frame_e2e(i):
+        if world == 1:
+            host_np[:] = 0                              # main.rs:73 clear
+            ctx.render_ptr(cam_structs[i], host_np.ctypes.data, W, H)   # splat_render: H2D + kernels + D2H, synchronous
+        else:
+            if r1 > r0:
+                my_host.zero_()
+                fb_dev[r0:r1].copy_(my_host[: r1 - r0], non_blocking=True)          # H2D of this rank's stripe
+                ctx.render_device(cam_structs[i], fb_dev[r0:r1].data_ptr(), W, H, r0, r1, stream.cuda_stream)
+            gather_frame()
+            if rank == 0:
+                host_fb.copy_(fb_dev, non_blocking=True)                             # D2H of the gathered frame
+            torch.cuda.synchronize()
+
+    off = Wm + K
+    for i in range(Wm):
+        frame_e2e(off + i)
+    sync_all()
+    t_e0 = time.perf_counter()
+    for i in range(Wm, Wm + K):
+        frame_e2e(off + i)
+    sync_all()
+    e2e_s = torch.tensor([time.perf_counter() - t_e0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_fps = K / float(e2e_s.item())
+    checksum = int(host_np.astype(np.uint64).sum()) if rank == 0 else 0
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        T = ((W + TILE - 1) // TILE) * ((r1 - r0 + TILE - 1) // TILE)
+        P = W * (r1 - r0)
+        I = inst_sum / K
+        blend_ms = stage["blend_ms"] / K
+        alg_bytes = 52.0 * I + 8.0 * T + 8.0 * P       # K5 = 52*I + 8*T + 8*P
+        achieved = alg_bytes / (blend_ms * 1e-3) / 1e9 if blend_ms > 0 else 0.0
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "blend_traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": "frames/sec at 1080p (6M Gaussians)", "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args, world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_fps, "unit": "frames/s",
+                    "h2d_bytes_per_step": W * H * 4 + 184, "d2h_bytes_per_step": W * H * 4 + 16},
+            "gpu_launches": int(lsum.item()),
+            "roofline": {"kernel": "blend_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": blend_ms,
+                         "note": "blend is FP32-issue bound (SURVEY F8): ~60 ops per pixel-Gaussian pair against "
+                                 "52 B per tile instance; the HBM fraction is reported because it is the contract metric"},
+            "stages_ms": {k_: v / K for k_, v in stage.items()},
+            "instances_per_frame": I, "frame_checksum": checksum,
+        }
+        if world == 1 and not args.no_cpu:
+            from oracle import oracle as orc
+            orc.build()
+            cores = os.cpu_count() or 1
+            cov3d = orc.compute_cov3d(sc.rotations, sc.scales)
+            row_step = args.cpu_row_step or 4
+            c = cpu_frame_time(orc, sc, cov3d, cams_all[Wm], W, H, row_step, cores)
+            line["cpu_baseline"] = {
+                "value": 1.0 / c["frame_s"], "unit": "frames/s", "cores": cores, "kind": "port",
+                "sample": (f"one frame of the same scene/camera: project+stable sort of all {n} Gaussians "
+                           f"({c['project_s']:.2f}s+{c['sort_s']:.2f}s) and the quad rasteriser on every {row_step}th 16-row "
+                           f"tile stripe ({c['rows_sampled']} of {H} rows, {c['raster_sample_s']:.2f}s, scaled x{c['scale']:.2f}); "
+                           "C restatement of the reference (oracle/), not the Rust/euc binary"),
+                "pairs_per_frame_est": c["pairs_in_rect_est"]}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=6_100_000)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--cpu-row-step", type=int, default=0, help="CPU sample: every k-th tile stripe (0 = default)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        log("[bench] warm-up raised to 3 (timing rules)")
+        args.warmup = 3
+    return run_reference(args) if args.impl == "reference" else run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -72,6 +72,10 @@ def lib():
         L.orc_rasterize.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(OrcConfig),
                                     C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                     C.POINTER(OrcStats)]
+        L.orc_rasterize_rowlist.restype = C.c_int
+        L.orc_rasterize_rowlist.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(OrcConfig),
+                                            C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32,
+                                            C.POINTER(OrcStats)]
         L.orc_render.restype = C.c_int
         L.orc_render.argtypes = [fp, fp, fp, fp, C.c_uint64, C.POINTER(OrcCamera),
                                  C.POINTER(OrcConfig), C.c_void_p, C.c_uint32, C.c_uint32,
@@ -156,6 +160,20 @@ def rasterize(splats, order, cfg, fb: np.ndarray, row0=0, row1=None):
                              fb.ctypes.data, W, H, row0, H if row1 is None else row1, C.byref(st))
     if rc:
         raise RuntimeError(f"orc_rasterize failed: {rc}")
+    return st
+
+
+def rasterize_rows(splats, order, cfg, fb: np.ndarray, rows):
+    """Blend onto an explicit ascending list of rows (bench.py's bounded CPU sample)."""
+    H, W = fb.shape
+    assert fb.dtype == np.uint32 and fb.flags["C_CONTIGUOUS"]
+    st = OrcStats()
+    order = np.ascontiguousarray(order, np.uint32)
+    rows = np.ascontiguousarray(rows, np.int32)
+    rc = lib().orc_rasterize_rowlist(splats.ctypes.data, order.ctypes.data, len(order), C.byref(cfg),
+                                     fb.ctypes.data, W, H, rows.ctypes.data, len(rows), C.byref(st))
+    if rc:
+        raise RuntimeError(f"orc_rasterize_rowlist failed: {rc}")
     return st
 
 
