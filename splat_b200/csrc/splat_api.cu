@@ -47,6 +47,7 @@ struct splat_ctx {
   uint64_t inst_cap = 0;
   uint32_t *ikeys[2] = {nullptr, nullptr}, *ivals[2] = {nullptr, nullptr};
   uint2 *ranges = nullptr; size_t ranges_cap = 0;
+  uint32_t *tile_order = nullptr;
   FrameStatus *d_status = nullptr, *h_status = nullptr;
   uint32_t *d_fb = nullptr; size_t fb_cap = 0;
 
@@ -234,7 +235,9 @@ int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cuda
   const uint32_t T = P.tiles_x * P.tiles_y;
   if (T > c->ranges_cap) {
     dev_free(c->ranges);
+    dev_free(c->tile_order);
     CU(dev_alloc(&c->ranges, T));
+    CU(dev_alloc(&c->tile_order, T));
     c->ranges_cap = T;
   }
   int icur = 0;
@@ -249,12 +252,13 @@ int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cuda
   CU(cudaMemsetAsync(c->ranges, 0, (size_t)T * sizeof(uint2), s));
   if (I > 0) {
     tile_ranges_kernel<<<cdiv(I, 256), 256, 0, s>>>(c->ikeys[icur], (uint32_t)I, c->ranges);
-    c->launches += 1;
+    tile_order_kernel<<<1, 1024, 0, s>>>(c->ranges, T, c->tile_order);   // heaviest tiles first
+    c->launches += 2;
   }
   CU(cudaEventRecord(c->ev[EV_RANGES], s));
   if (wait_ev) CU(cudaStreamWaitEvent(s, wait_ev, 0));
   if (I > 0) {
-    blend_kernel<<<dim3(P.tiles_x, P.tiles_y), BL_THREADS, 0, s>>>(c->ranges, c->ivals[icur], c->recs, fb_rows_dev, P);
+    blend_kernel<<<2 * T, BL_THREADS, 0, s>>>(c->ranges, c->tile_order, c->ivals[icur], c->recs, fb_rows_dev, P);
     c->launches += 1;
   }
   CU(cudaEventRecord(c->ev[EV_BLEND], s));
@@ -312,7 +316,7 @@ void splat_destroy(splat_ctx *c) {
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_scene(c);
-  dev_free(c->hist); dev_free(c->partial); dev_free(c->ranges); dev_free(c->d_status); dev_free(c->d_fb);
+  dev_free(c->hist); dev_free(c->partial); dev_free(c->ranges); dev_free(c->tile_order); dev_free(c->d_status); dev_free(c->d_fb);
   for (int k = 0; k < 2; ++k) { dev_free(c->ikeys[k]); dev_free(c->ivals[k]); }
   if (c->h_status) cudaFreeHost(c->h_status);
   for (int i = 0; i < EV_COUNT_; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
