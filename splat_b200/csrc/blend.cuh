@@ -86,11 +86,11 @@ SPLAT_DEVINL void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware instead of polling
       : "memory");
 }
 SPLAT_DEVINL void producers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(BL_PRODUCER_THREADS) : "memory"); }
@@ -186,6 +186,38 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint32_t *__restrict__ orde
         }
 #pragma unroll
         for (int q = 0; q < BL_GROUPS; ++q) bits |= (((ox >> (q & 1)) & (oy >> (q >> 1))) & 1u) << q;
+        // Second, tighter test: can ANY sample of the group reach power >= pth?  power = -q/2
+        // with q(dx,dy) = A dx^2 + 2B dx dy + C dy^2; for a positive-definite conic the minimum
+        // of q over the group's sample rectangle is 0 if the centre is inside, else it lies on
+        // one of the four edges (1-D clamped minimisation).  The bound is evaluated in f32
+        // with a relative slack 100x above its rounding error, so it never removes a pair
+        // that the exact per-pixel test would accept.  (The alpha byte, which also depends
+        // on non-contributing covered entries, is resolved separately by the consumer.)
+        const float cA = a.z, cB = a.w, cC = b.x, pth = c.w;
+        if (pth > 0.0f) bits = 0;   // opacity < 1/255: power <= 0 < pth can never pass
+        if (bits && cA > 0.0f && cC > 0.0f && cA * cC - cB * cB > 0.0f) {
+          const float invA = __fdiv_rn(1.0f, cA), invC = __fdiv_rn(1.0f, cC);
+#pragma unroll
+          for (int q = 0; q < BL_GROUPS; ++q) {
+            if (!((bits >> q) & 1u)) continue;
+            const float xl = sxl[q & 1] - a.x, xh = sxh[q & 1] - a.x;
+            const float yl = syl[q >> 1] - a.y, yh = syh[q >> 1] - a.y;
+            if (xl <= 0.0f && xh >= 0.0f && yl <= 0.0f && yh >= 0.0f) continue;   // centre inside
+            float qmin = 3.0e38f;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const float x0 = e ? xh : xl;
+              const float ty = fminf(fmaxf(-cB * x0 * invC, yl), yh);
+              qmin = fminf(qmin, cA * x0 * x0 + (2.0f * cB * x0 + cC * ty) * ty);
+              const float y0 = e ? yh : yl;
+              const float tx = fminf(fmaxf(-cB * y0 * invA, xl), xh);
+              qmin = fminf(qmin, cC * y0 * y0 + (2.0f * cB * y0 + cA * tx) * tx);
+            }
+            const float xm = fmaxf(fabsf(xl), fabsf(xh)), ym = fmaxf(fabsf(yl), fabsf(yh));
+            const float slack = 1e-5f * (cA * xm * xm + cC * ym * ym + 2.0f * fabsf(cB) * xm * ym) + 1e-4f;
+            if (!(0.5f * qmin <= -pth + slack)) bits &= ~(1u << q);
+          }
+        }
       }
       uint32_t rank[BL_GROUPS];
 #pragma unroll
@@ -218,6 +250,7 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint32_t *__restrict__ orde
         if ((chunk & 1u) != p) { s = chunk_end; continue; }
         const uint32_t slot = chunk % BL_D;
         if (s % BL_CH == 0) mbar_wait(&S.empty[g][slot], ((chunk / BL_D) & 1u) ^ 1u);
+        float *slotp = &S.ring[g][slot][s % BL_CH][0];
         for (; s < chunk_end; ++s) {
           const uint32_t j = S.list[g][s - seq];
           const float4 a = S.sa[j], b = S.sb[j], c = S.sc[j];
@@ -229,17 +262,15 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint32_t *__restrict__ orde
           const float q3 = __fmul_rn(__fmul_rn(a.w, dx), dy);
           const float power = __fsub_rn(__fmul_rn(-0.5f, __fadd_rn(q1, q2)), q3);
           const bool cand = inr && !(power > 0.0f) && (power >= c.w);
-          // E7: a covered pixel whose fragment is zero still gets its alpha byte reset (0);
-          // an uncovered pixel (-1) is left alone
-          float val = inr ? 0.0f : -1.0f;
+          float val = 0.0f;   // zero fragment: RGB unchanged (its alpha-byte effect: see consumer)
           if (__any_sync(0xFFFFFFFFu, cand)) {
             const float ex = expf_pinned(power);
             const float al = fminf(0.99f, __fmul_rn(b.y, ex));     // pipelines.rs:139
             if (cand && !(al < (1.0f / 255.0f))) val = al;          // pipelines.rs:140
           }
-          float *slotp = &S.ring[g][slot][s % BL_CH][0];
           slotp[lane] = val;
-          if (lane == 0) *reinterpret_cast<float4 *>(slotp + 32) = make_float4(c.x, c.y, c.z, 0.0f);
+          if (lane == 0) *reinterpret_cast<float4 *>(slotp + 32) = c;   // rgb (+ threshold, unused)
+          slotp += BL_SLOT_F;
         }
         if (chunk_end % BL_CH == 0) {
           __syncwarp();
@@ -276,7 +307,32 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint32_t *__restrict__ orde
     float cr = div255((float)((old >> 16) & 0xFFu));
     float cg = div255((float)((old >> 8) & 0xFFu));
     float cb = div255((float)(old & 0xFFu));
-    float last_alpha = -1.0f;   // < 0: no quad covered this pixel yet
+    // E7 (alpha byte).  blend() stores the CURRENT fragment's alpha, and euc calls it for every
+    // covered pixel, so the byte a pixel ends up with belongs to the LAST entry of the list
+    // whose 3-sigma rectangle covers it -- 0 if that fragment was zero.  That entry is found
+    // here by walking the list backwards (typically a few dozen entries) while the producers
+    // fill the ring; the main loop then only has to handle entries that change RGB.
+    const float sx = (float)px + P.sample_off, sy = (float)py + P.sample_off;
+    uint32_t last_g = 0xFFFFFFFFu;
+    bool found = !inside;
+    for (uint32_t end = range.y; end > range.x && __any_sync(0xFFFFFFFFu, !found); end -= min(32u, end - range.x)) {
+      const uint32_t cntb = min(32u, end - range.x);
+      uint32_t gi = 0;
+      float ecx = 0.f, ecy = 0.f, ehx = -1.f, ehy = -1.f;
+      if (lane < cntb) {
+        gi = __ldg(&inst_vals[end - 1u - lane]);
+        const float4 *rp = reinterpret_cast<const float4 *>(recs + gi);
+        const float4 a = __ldg(rp), b = __ldg(rp + 1);
+        ecx = a.x; ecy = a.y; ehx = b.z; ehy = b.w;
+      }
+      for (uint32_t k = 0; k < cntb; ++k) {
+        const float kx = __shfl_sync(0xFFFFFFFFu, ecx, k), ky = __shfl_sync(0xFFFFFFFFu, ecy, k);
+        const float khx = __shfl_sync(0xFFFFFFFFu, ehx, k), khy = __shfl_sync(0xFFFFFFFFu, ehy, k);
+        const uint32_t kg = __shfl_sync(0xFFFFFFFFu, gi, k);
+        if (!found && fabsf(sx - kx) <= khx && fabsf(sy - ky) <= khy) { found = true; last_g = kg; }
+        if (!__any_sync(0xFFFFFFFFu, !found)) break;
+      }
+    }
 
     for (uint32_t chunk = 0;; ++chunk) {
       const uint32_t slot = chunk % BL_D;
@@ -295,17 +351,30 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint32_t *__restrict__ orde
             cb = blend_channel(cb, om, __fmul_rn(al, col.z));
           }
         }
-        last_alpha = (al >= 0.0f) ? al : last_alpha;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.empty[g][slot]);
       if (h & 0x100u) break;
     }
 
-    if (inside && last_alpha >= 0.0f) {
+    if (inside && last_g != 0xFFFFFFFFu) {
+      // fragment() of the last covering entry for this pixel (pipelines.rs:127-145)
+      const float4 *rp = reinterpret_cast<const float4 *>(recs + last_g);
+      const float4 a = __ldg(rp), b = __ldg(rp + 1);
+      const float dx = sx - a.x, dy = sy - a.y;
+      const float q1 = __fmul_rn(__fmul_rn(a.z, dx), dx);
+      const float q2 = __fmul_rn(__fmul_rn(b.x, dy), dy);
+      const float q3 = __fmul_rn(__fmul_rn(a.w, dx), dy);
+      const float power = __fsub_rn(__fmul_rn(-0.5f, __fadd_rn(q1, q2)), q3);
+      float last_alpha = 0.0f;
+      if (!(power > 0.0f)) {
+        const float ex = (power >= -87.0f) ? expf_pinned(power) : 0.0f;   // splat_expf flushes below -87
+        const float t = fminf(0.99f, __fmul_rn(b.y, ex));
+        if (!(t < (1.0f / 255.0f))) last_alpha = t;
+      }
       const uint32_t r = (uint32_t)__fmul_rn(cr, 255.0f), gg = (uint32_t)__fmul_rn(cg, 255.0f);
-      const uint32_t bl = (uint32_t)__fmul_rn(cb, 255.0f), a = (uint32_t)__fmul_rn(last_alpha, 255.0f);
-      *pix = bl | (gg << 8) | (r << 16) | (a << 24);
+      const uint32_t bl = (uint32_t)__fmul_rn(cb, 255.0f), av = (uint32_t)__fmul_rn(last_alpha, 255.0f);
+      *pix = bl | (gg << 8) | (r << 16) | (av << 24);
     }
   }
 }
