@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsplat_b200.so")
+# SPLAT_B200_LIB overrides the path (kernel experiments build variant libraries side by side)
+LIB_PATH = os.environ.get("SPLAT_B200_LIB") or os.path.join(_HERE, "libsplat_b200.so")
 
 SPLAT_OK = 0
 ERRORS = {-1: "SPLAT_ERR_INVALID", -2: "SPLAT_ERR_CUDA", -3: "SPLAT_ERR_NOMEM",

@@ -9,38 +9,87 @@
 // covering Gaussian in order and must reproduce the f32 operation sequence exactly:
 //   old = byte / 255           (IEEE division; here a 2-op fmaf form, exact for all 256 bytes)
 //   out = (1-a)*old + a*new    (two products, one add, no FMA)
-//   byte' = trunc_sat(out*255) (saturating add + round-toward-zero add of 2^23)
+//   byte' = trunc_sat(out*255) (round-toward-zero add of 2^23)
 // exp() is the pinned "splat_expf v1" sequence shared with the oracle (oracle/splat_oracle.c).
 //
-// Work decomposition (r1b; the first version -- one 8-warp CTA per tile, every warp doing
-// alpha AND blend -- left the SMs 45% idle because tile lists are extremely skewed: the
-// heaviest tile holds 275k of 48M instances and its 8 sequential warp streams were the frame's
-// critical path):
-//   * work unit = half a 16x16 tile (16x8 pixels); units are issued heaviest-first
-//     (tile_order_kernel) so the long units start at t=0 and short ones fill the tail;
-//   * per 8x4-pixel group a TEAM of three warps: two PRODUCER warps evaluate
-//     fragment() -- coverage, power, exp, alpha -- for alternating chunks of 8 list entries and
-//     publish one alpha per pixel (+ the entry's colour) into a shared-memory ring; one
-//     CONSUMER warp runs only the strictly sequential blend() chain.  Producers and consumer
-//     hand chunks over through mbarriers (full/empty per ring slot), so the per-pixel chain is
-//     ~36 instructions per entry instead of ~80 and the independent part runs ahead of it;
-//   * the unit's sorted list is staged through shared memory 256 entries at a time by the 8
+// The kernel is bound by the FP32 pipe (about 45 IEEE operations per pixel-Gaussian pair, 3.8e9
+// contributing pairs per 1080p frame of the 6.1M scene), not by HBM, so the design minimises
+// issue slots and FMA-pipe cycles per pair:
+//   * every lane owns TWO pixels (x, y) and (x, y+4) and evaluates them with Blackwell's packed
+//     f32x2 instructions (FFMA2 / FMUL2 / FADD2: two IEEE-rounded results per lane per issue
+//     slot; measured in tools/microbench: same FLOP rate as scalar, half the instructions);
+//   * a 16x16 tile = four 8x8-pixel groups.  Tile lists are extremely skewed (in the 6.1M scene
+//     119 of 8160 tiles hold 42% of all tile instances and the longest list is 0.6% of the
+//     frame, about what one of the 148 SMs can process in the whole frame time), so a work
+//     unit is a tile, half a tile or a single group depending on the list length
+//     (unit_order_kernel); units are issued heaviest-first so the long lists start at t=0 and
+//     short ones fill the tail;
+//   * per group a TEAM: 2, 4 or 8 PRODUCER warps (8 per CTA, shared among the unit's groups)
+//     evaluate fragment() -- coverage, power, exp, alpha -- for alternating chunks of 8 list
+//     entries and publish the entries that change at least one pixel (two alphas per lane +
+//     the colour) into a shared-memory ring; one CONSUMER warp runs only the strictly
+//     sequential blend() chain (28 FMA-pipe instructions per entry).  Hand-over through
+//     mbarriers (full/empty per ring slot);
+//   * the tile's sorted list is staged through shared memory 256 entries at a time by the 8
 //     producer warps (one entry per thread), which also compact, per group, the indices of
-//     the entries whose 3-sigma rectangle can touch that group's 32 pixels.
+//     the entries whose 3-sigma rectangle and alpha >= 1/255 ellipse can touch the group.
+//
+// ptxas contracts mul.f32x2 + add.f32x2 into FFMA2 even under --fmad=false (seen in SASS), which
+// would change roundings.  Every packed product that feeds an addition is therefore written as
+// fma(a, b, nz) with nz = (-0.0, -0.0) read from the kernel parameters at run time: a*b + (-0)
+// is exactly RN(a*b), and ptxas can neither fold the unknown addend nor fuse an FMA with an add.
 #pragma once
 #include "common.cuh"
 
 namespace splat {
 
-constexpr int BL_GROUPS = 4;                       // 8x4-pixel groups per CTA (16x8 pixels)
+constexpr int BL_GROUPS = 4;                       // 8x8-pixel groups per CTA (one 16x16 tile)
 constexpr int BL_PRODUCER_THREADS = 256;           // 8 producer warps: team = warp>>1, p = warp&1
 constexpr int BL_THREADS = BL_PRODUCER_THREADS + 32 * BL_GROUPS;   // + one consumer warp per team
 constexpr int BL_BATCH = 256;                      // list entries staged per round
-constexpr int BL_CH = 8;                           // entries per ring chunk
-constexpr int BL_D = 4;                            // ring depth in chunks (2 per producer)
-constexpr int BL_SLOT_F = 36;                      // floats per ring entry: 32 alphas + rgb + pad
+constexpr int BL_CH = 8;                           // list entries per ring chunk
+constexpr int BL_SLOTS = 16;                       // ring chunk slots per CTA, split among the unit's groups
 
-// splat_expf v1 on its hot domain [-87, 0] (callers guarantee the domain).
+// ---------------------------------------------------------------- packed f32x2 helpers
+typedef unsigned long long f32x2;   // two IEEE binary32 values in one 64-bit register pair
+
+SPLAT_DEVINL f32x2 pk(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+SPLAT_DEVINL f32x2 pk1(float v) { return pk(v, v); }
+SPLAT_DEVINL void upk(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+SPLAT_DEVINL f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+// product that does NOT feed an addition (safe to leave as FMUL2)
+SPLAT_DEVINL f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// product that feeds an addition: a*b + (-0) == RN(a*b), unfusable (see header)
+SPLAT_DEVINL f32x2 mul2x(f32x2 a, f32x2 b, f32x2 nz) { return fma2(a, b, nz); }
+SPLAT_DEVINL f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+SPLAT_DEVINL f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+SPLAT_DEVINL f32x2 add2_rz(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// splat_expf v1 on its hot domain [-87, 0] (callers guarantee the domain), scalar and packed.
 SPLAT_DEVINL float expf_pinned(float x) {
   const float MAGIC = 12582912.0f;
   const float tm = __fmaf_rn(x, 0x1.715476p+0f, MAGIC);
@@ -56,12 +105,30 @@ SPLAT_DEVINL float expf_pinned(float x) {
   p = __fmaf_rn(p, r, 1.0f);
   return __uint_as_float(__float_as_uint(p) + (__float_as_uint(tm) << 23));
 }
+SPLAT_DEVINL void expf2_pinned(f32x2 x, float &e0, float &e1) {
+  const f32x2 MAGIC = pk1(12582912.0f);
+  const f32x2 tm = fma2(x, pk1(0x1.715476p+0f), MAGIC);
+  const f32x2 n = sub2(tm, MAGIC);
+  f32x2 r = fma2(n, pk1(-0x1.62e4p-1f), x);
+  r = fma2(n, pk1(-0x1.7f7d1cp-20f), r);
+  f32x2 p = pk1(0x1.687b46p-10f);
+  p = fma2(p, r, pk1(0x1.123bdcp-7f));
+  p = fma2(p, r, pk1(0x1.555b5cp-5f));
+  p = fma2(p, r, pk1(0x1.55548ep-3f));
+  p = fma2(p, r, pk1(0x1.fffff8p-2f));
+  p = fma2(p, r, pk1(1.0f));
+  p = fma2(p, r, pk1(1.0f));
+  float p0, p1, t0, t1;
+  upk(p, p0, p1);
+  upk(tm, t0, t1);
+  e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+  e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+}
 
 // byte / 255.0f, correctly rounded for every integer 0..255 (checked exhaustively in
 // tests/test_host_math.py): q = fma(n, RN(1/255), n * (1/255 - RN(1/255))).
-SPLAT_DEVINL float div255(float n) {
-  return __fmaf_rn(n, 0x1.010102p-8f, __fmul_rn(n, -0x1.fdfdfep-33f));
-}
+constexpr float DIV255_HI = 0x1.010102p-8f, DIV255_LO = -0x1.fdfdfep-33f;
+SPLAT_DEVINL float div255(float n) { return __fmaf_rn(n, DIV255_HI, __fmul_rn(n, DIV255_LO)); }
 
 // One channel of blend(): returns the new channel state (= new byte / 255).
 // `as u8` saturates and maps NaN to 0: trunc_sat(out*255) == trunc(sat01(out)*255), because
@@ -71,6 +138,19 @@ SPLAT_DEVINL float blend_channel(float c_old, float om, float u) {
   const float v = __fmul_rn(out, 255.0f);
   const float byte = __fsub_rn(__fadd_rz(v, 8388608.0f), 8388608.0f);  // truncate toward zero
   return div255(byte);
+}
+// Two pixels of one channel.  Products and the truncation chain are packed; the addition is
+// issued as two scalar FADD.SAT because f32x2 has no saturating form (same FMA-pipe cycles as
+// one FADD2, one more issue slot) -- colours are not clamped by the reference (gaussians.rs:97),
+// so out can leave [0,1] and `as u8` saturates.
+SPLAT_DEVINL f32x2 blend_channel2(f32x2 c_old, f32x2 om, f32x2 al, float col, f32x2 nz) {
+  float t0, t1, u0, u1;
+  upk(mul2x(om, c_old, nz), t0, t1);
+  upk(mul2x(al, pk1(col), nz), u0, u1);
+  const f32x2 out = pk(__saturatef(__fadd_rn(t0, u0)), __saturatef(__fadd_rn(t1, u1)));
+  const f32x2 v = mul2x(out, pk1(255.0f), nz);
+  const f32x2 n = sub2(add2_rz(v, pk1(8388608.0f)), pk1(8388608.0f));
+  return fma2(n, pk1(DIV255_HI), mul2(n, pk1(DIV255_LO)));
 }
 
 // ---------------------------------------------------------------- mbarrier / named barrier
@@ -82,90 +162,157 @@ SPLAT_DEVINL void mbar_arrive(uint64_t *bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.release.cta.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar))
                : "memory");
 }
+// Blocking wait.  SPIN = false: try_wait with a suspend-time hint (the warp sleeps in hardware
+// and stops taking issue slots); SPIN = true: test_wait polling (lowest wake-up latency).
+template <bool SPIN>
 SPLAT_DEVINL void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1, %2;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-      "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware instead of polling
-      : "memory");
+  if (SPIN) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.test_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(0x989680u)
+        : "memory");
+  }
 }
+#ifndef SPLAT_SPIN_CONSUMER
+#define SPLAT_SPIN_CONSUMER true
+#endif
+#ifndef SPLAT_SPIN_PRODUCER
+#define SPLAT_SPIN_PRODUCER false
+#endif
 SPLAT_DEVINL void producers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(BL_PRODUCER_THREADS) : "memory"); }
 
 // ---------------------------------------------------------------- heaviest-first unit order
-// order[rank] = tile id, tiles sorted by descending list length (bucketed on 16*log2(len)):
-// single CTA counting sort.  Also publishes nothing else; empty tiles end up last.
+// A unit is (tile, first group, number of groups): 4 groups = whole tile, 2 = upper / lower half,
+// 1 = a single 8x8 group.  unit.y = ngroups | first_group << 8.  Tiles are ordered by descending
+// list length (counting sort on 16*log2(len) buckets, single CTA); a tile whose list is longer
+// than 1/3200 (1/800) of the frame's instances is split into 2 (4) units, which then run on
+// different SMs with 4 (8) producer warps per group.  Empty tiles produce no unit.
+SPLAT_DEVINL uint32_t unit_split(uint32_t len, uint32_t t2, uint32_t t4) { return len > t4 ? 4u : (len > t2 ? 2u : 1u); }
+
 __global__ void __launch_bounds__(1024)
-tile_order_kernel(const uint2 *__restrict__ ranges, uint32_t T, uint32_t *__restrict__ order) {
+unit_order_kernel(const uint2 *__restrict__ ranges, uint32_t T, uint2 *__restrict__ units,
+                  uint32_t *__restrict__ n_units, const unsigned long long *__restrict__ n_instances) {
   constexpr int NB = 512;
   __shared__ uint32_t hist[NB];
   for (int i = threadIdx.x; i < NB; i += blockDim.x) hist[i] = 0;
   __syncthreads();
-  auto bucket = [](uint2 r) -> uint32_t {
-    const uint32_t len = r.y > r.x ? r.y - r.x : 0u;
-    if (len == 0) return NB - 1;
+  const unsigned long long I = *n_instances;
+  const uint32_t t4 = (uint32_t)max(4096ull, I / 800ull), t2 = (uint32_t)max(2048ull, I / 3200ull);
+  auto bucket = [](uint32_t len) -> uint32_t {
     const int b = (int)(16.0f * __log2f((float)len));   // 0 .. 16*32-1
-    return (uint32_t)max(0, NB - 2 - b);
+    return (uint32_t)max(0, NB - 1 - b);
   };
-  for (uint32_t t = threadIdx.x; t < T; t += blockDim.x) atomicAdd(&hist[bucket(ranges[t])], 1u);
+  for (uint32_t t = threadIdx.x; t < T; t += blockDim.x) {
+    const uint2 r = ranges[t];
+    if (r.y > r.x) atomicAdd(&hist[bucket(r.y - r.x)], unit_split(r.y - r.x, t2, t4));
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t run = 0;
     for (int i = 0; i < NB; ++i) { const uint32_t c = hist[i]; hist[i] = run; run += c; }
+    *n_units = run;
   }
   __syncthreads();
-  for (uint32_t t = threadIdx.x; t < T; t += blockDim.x) order[atomicAdd(&hist[bucket(ranges[t])], 1u)] = t;
+  for (uint32_t t = threadIdx.x; t < T; t += blockDim.x) {
+    const uint2 r = ranges[t];
+    if (r.y <= r.x) continue;
+    const uint32_t nu = unit_split(r.y - r.x, t2, t4), ng = 4u / nu;
+    const uint32_t pos = atomicAdd(&hist[bucket(r.y - r.x)], nu);
+    for (uint32_t k = 0; k < nu; ++k) units[pos + k] = make_uint2(t, ng | ((k * ng) << 8));
+  }
 }
 
 // ---------------------------------------------------------------- K5
+struct RingEntry {
+  float2 al[32];   // per lane: alpha of pixel (x, y) and of pixel (x, y+4); 0 = no change
+  float4 col;      // r, g, b (+ the power threshold, unused by the consumer)
+};
 struct BlendSmem {
   float4 sa[BL_BATCH], sb[BL_BATCH], sc[BL_BATCH];        // staged records (see Rec)
-  float ring[BL_GROUPS][BL_D][BL_CH][BL_SLOT_F];          // per team: alpha per pixel + colour
-  uint64_t full[BL_GROUPS][BL_D], empty[BL_GROUPS][BL_D]; // mbarriers
-  uint32_t hdr[BL_GROUPS][BL_D];                          // entries in the chunk | last << 8
+  RingEntry ring[BL_SLOTS][BL_CH];                        // chunk slots, BL_SLOTS / ngroups per team
+  uint64_t full[BL_SLOTS], empty[BL_SLOTS];               // mbarriers
+  uint32_t hdr[BL_SLOTS];                                 // entries in the chunk | last << 8
   uint32_t wcount[BL_GROUPS][BL_PRODUCER_THREADS / 32];   // per staging warp, per group
   uint8_t list[BL_GROUPS][BL_BATCH];                      // compacted entry indices per group
 };
+constexpr size_t BL_SMEM_BYTES = sizeof(BlendSmem);
+
+// fragment() for one pixel against one record (pipelines.rs:127-145), used by the epilogue
+SPLAT_DEVINL float fragment_alpha(float sx, float sy, const float4 a, const float4 b) {
+  const float dx = sx - a.x, dy = sy - a.y;
+  const float q1 = __fmul_rn(__fmul_rn(a.z, dx), dx);
+  const float q2 = __fmul_rn(__fmul_rn(b.x, dy), dy);
+  const float q3 = __fmul_rn(__fmul_rn(a.w, dx), dy);
+  const float power = __fsub_rn(__fmul_rn(-0.5f, __fadd_rn(q1, q2)), q3);
+  float alpha = 0.0f;
+  if (!(power > 0.0f)) {
+    const float ex = (power >= -87.0f) ? expf_pinned(power) : 0.0f;   // splat_expf flushes below -87
+    const float t = fminf(0.99f, __fmul_rn(b.y, ex));
+    if (!(t < (1.0f / 255.0f))) alpha = t;
+  }
+  return alpha;
+}
 
 __global__ void __launch_bounds__(BL_THREADS, 3)
-blend_kernel(const uint2 *__restrict__ ranges, const uint32_t *__restrict__ order,
-             const uint32_t *__restrict__ inst_vals, const Rec *__restrict__ recs,
+blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
+             const uint32_t *__restrict__ n_units, const uint32_t *__restrict__ inst_vals, const Rec *__restrict__ recs,
              uint32_t *__restrict__ fb_rows, const __grid_constant__ FrameParams P) {
-  __shared__ BlendSmem S;
+  extern __shared__ __align__(16) unsigned char blend_smem_raw[];
+  BlendSmem &S = *reinterpret_cast<BlendSmem *>(blend_smem_raw);
 
-  const uint32_t tile = order[blockIdx.x >> 1], half = blockIdx.x & 1u;
+  if (blockIdx.x >= *n_units) return;   // tiles nothing touches have no unit: pixels stay as they are
+  const uint2 unit = units[blockIdx.x];
+  const uint32_t tile = unit.x, ng = unit.y & 0xFFu, g0 = unit.y >> 8;     // ng in {1, 2, 4}
+  const uint32_t lg_ng = ng >> 1;                                          // log2(ng)
+  const uint32_t ppg_log = 3u - lg_ng, ppg_mask = (1u << ppg_log) - 1u;    // producers per group
+  const uint32_t d_log = 4u - lg_ng, d_mask = (1u << d_log) - 1u;          // chunk slots per group
   const uint2 range = ranges[tile];
-  if (range.y <= range.x) return;   // nothing touches this tile: pixels stay as they are
   const uint32_t tile_x = tile % P.tiles_x, tile_y = tile / P.tiles_x;
-  const uint32_t tx0 = tile_x * TILE, ty0 = (P.tile_y0 + tile_y) * TILE + 8u * half;
-  if (ty0 >= P.row1) return;        // lower half of a ragged last tile row
+  const uint32_t tx0 = tile_x * TILE, ty0 = (P.tile_y0 + tile_y) * TILE;
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
-  if (tid < BL_GROUPS * BL_D) {
-    mbar_init(&S.full[tid / BL_D][tid % BL_D], 1);
-    mbar_init(&S.empty[tid / BL_D][tid % BL_D], 1);
+  if (tid < BL_SLOTS) {
+    mbar_init(&S.full[tid], 1);
+    mbar_init(&S.empty[tid], 1);
   }
   __syncthreads();
+  const f32x2 NZ = P.nz2;
 
   if (w < BL_PRODUCER_THREADS / 32) {
     // ============================== PRODUCERS ==============================
-    const uint32_t g = w >> 1, p = w & 1u;
+    const uint32_t gl = w >> ppg_log, p = w & ppg_mask, g = g0 + gl;   // local team, rank in team, group
+    const uint32_t unit_mask = ((1u << ng) - 1u) << g0;
     const float sx = (float)(tx0 + 8u * (g & 1u) + (lane & 7u)) + P.sample_off;
-    const float sy = (float)(ty0 + 4u * (g >> 1) + (lane >> 3)) + P.sample_off;
+    const float sy0 = (float)(ty0 + 8u * (g >> 1) + (lane >> 3)) + P.sample_off;
+    const float sy1 = (float)(ty0 + 8u * (g >> 1) + (lane >> 3) + 4u) + P.sample_off;
+    const f32x2 sy2 = pk(sy0, sy1);
     // group sample intervals for the overlap test (same (float)p + off as sx/sy)
     float sxl[2], sxh[2], syl[2], syh[2];
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       sxl[q] = (float)(tx0 + 8u * q) + P.sample_off;
       sxh[q] = (float)(tx0 + 8u * q + 7u) + P.sample_off;
-      syl[q] = (float)(ty0 + 4u * q) + P.sample_off;
-      syh[q] = (float)(ty0 + 4u * q + 3u) + P.sample_off;
+      syl[q] = (float)(ty0 + 8u * q) + P.sample_off;
+      syh[q] = (float)(ty0 + 8u * q + 7u) + P.sample_off;
     }
     const uint32_t lt_mask = (1u << lane) - 1u;
-    uint32_t seq = 0;   // entries of this team published so far (both producers count alike)
+    uint32_t seq = 0;    // list entries of this team handed out so far (both producers count alike)
+    uint32_t nout = 0;   // entries written into the chunk this producer is filling
 
     for (uint32_t base = range.x; base < range.y; base += BL_BATCH) {
       const uint32_t nb = min((uint32_t)BL_BATCH, range.y - base);
@@ -186,6 +333,7 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint32_t *__restrict__ orde
         }
 #pragma unroll
         for (int q = 0; q < BL_GROUPS; ++q) bits |= (((ox >> (q & 1)) & (oy >> (q >> 1))) & 1u) << q;
+        bits &= unit_mask;
         // Second, tighter test: can ANY sample of the group reach power >= pth?  power = -q/2
         // with q(dx,dy) = A dx^2 + 2B dx dy + C dy^2; for a positive-definite conic the minimum
         // of q over the group's sample rectangle is 0 if the centre is inside, else it lies on
@@ -222,6 +370,8 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint32_t *__restrict__ orde
       uint32_t rank[BL_GROUPS];
 #pragma unroll
       for (int q = 0; q < BL_GROUPS; ++q) {
+        rank[q] = 0;
+        if (!((unit_mask >> q) & 1u)) continue;
         const uint32_t bal = __ballot_sync(0xFFFFFFFFu, (bits >> q) & 1u);
         rank[q] = __popc(bal & lt_mask);
         if (lane == 0) S.wcount[q][w] = __popc(bal);
@@ -230,6 +380,7 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint32_t *__restrict__ orde
       uint32_t n_mine = 0;
 #pragma unroll
       for (int q = 0; q < BL_GROUPS; ++q) {
+        if (!((unit_mask >> q) & 1u)) continue;
         uint32_t before = 0, total = 0;
 #pragma unroll
         for (int ww = 0; ww < BL_PRODUCER_THREADS / 32; ++ww) {
@@ -247,36 +398,54 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint32_t *__restrict__ orde
       while (s < s_end) {
         const uint32_t chunk = s / BL_CH;
         const uint32_t chunk_end = min(s_end, (chunk + 1) * BL_CH);
-        if ((chunk & 1u) != p) { s = chunk_end; continue; }
-        const uint32_t slot = chunk % BL_D;
-        if (s % BL_CH == 0) mbar_wait(&S.empty[g][slot], ((chunk / BL_D) & 1u) ^ 1u);
-        float *slotp = &S.ring[g][slot][s % BL_CH][0];
+        if ((chunk & ppg_mask) != p) { s = chunk_end; continue; }
+        const uint32_t slot = (gl << d_log) + (chunk & d_mask);
+        if (s % BL_CH == 0) {
+          mbar_wait<SPLAT_SPIN_PRODUCER>(&S.empty[slot], ((chunk >> d_log) & 1u) ^ 1u);
+          nout = 0;
+        }
+        RingEntry *slotp = &S.ring[slot][nout];
+#pragma unroll 2
         for (; s < chunk_end; ++s) {
           const uint32_t j = S.list[g][s - seq];
           const float4 a = S.sa[j], b = S.sb[j], c = S.sc[j];
-          const float dx = sx - a.x, dy = sy - a.y;
-          const bool inr = (fabsf(dx) <= b.z) && (fabsf(dy) <= b.w);
-          // pipelines.rs:134, left to right, no FMA
-          const float q1 = __fmul_rn(__fmul_rn(a.z, dx), dx);
-          const float q2 = __fmul_rn(__fmul_rn(b.x, dy), dy);
-          const float q3 = __fmul_rn(__fmul_rn(a.w, dx), dy);
-          const float power = __fsub_rn(__fmul_rn(-0.5f, __fadd_rn(q1, q2)), q3);
-          const bool cand = inr && !(power > 0.0f) && (power >= c.w);
-          float val = 0.0f;   // zero fragment: RGB unchanged (its alpha-byte effect: see consumer)
-          if (__any_sync(0xFFFFFFFFu, cand)) {
-            const float ex = expf_pinned(power);
-            const float al = fminf(0.99f, __fmul_rn(b.y, ex));     // pipelines.rs:139
-            if (cand && !(al < (1.0f / 255.0f))) val = al;          // pipelines.rs:140
-          }
-          slotp[lane] = val;
-          if (lane == 0) *reinterpret_cast<float4 *>(slotp + 32) = c;   // rgb (+ threshold, unused)
-          slotp += BL_SLOT_F;
+          const float dx = sx - a.x;
+          const f32x2 dy2 = sub2(sy2, pk1(a.y));
+          float dy0, dy1;
+          upk(dy2, dy0, dy1);
+          const bool inx = fabsf(dx) <= b.z;
+          // pipelines.rs:134, left to right, no FMA: (A*dx)*dx, (C*dy)*dy, (B*dx)*dy
+          const float adx = __fmul_rn(a.z, dx), bdx = __fmul_rn(a.w, dx);
+          const float q1 = __fmul_rn(adx, dx);
+          const f32x2 q2 = mul2x(mul2(pk1(b.x), dy2), dy2, NZ);
+          const f32x2 q3 = mul2x(pk1(bdx), dy2, NZ);
+          const f32x2 pw2 = sub2(mul2x(add2(pk1(q1), q2), pk1(-0.5f), NZ), q3);
+          float pw0, pw1;
+          upk(pw2, pw0, pw1);
+          const bool cand0 = inx && (fabsf(dy0) <= b.w) && !(pw0 > 0.0f) && (pw0 >= c.w);
+          const bool cand1 = inx && (fabsf(dy1) <= b.w) && !(pw1 > 0.0f) && (pw1 >= c.w);
+          // straight-line on purpose (no warp-uniform early-outs): lets the compiler interleave
+          // the dependent chains of consecutive entries.  Non-candidate lanes compute a garbage
+          // exp that the selects below discard.
+          float e0, e1;
+          expf2_pinned(pw2, e0, e1);
+          const float al0 = fminf(0.99f, __fmul_rn(b.y, e0));     // pipelines.rs:139
+          const float al1 = fminf(0.99f, __fmul_rn(b.y, e1));
+          // zero fragment: RGB unchanged (alpha byte: see consumer)         pipelines.rs:140
+          const float v0 = (cand0 && !(al0 < (1.0f / 255.0f))) ? al0 : 0.0f;
+          const float v1 = (cand1 && !(al1 < (1.0f / 255.0f))) ? al1 : 0.0f;
+          slotp->al[lane] = make_float2(v0, v1);
+          if (lane == 0) slotp->col = c;
+          // entries that change no pixel of the group are overwritten by the next one
+          const uint32_t adv = __any_sync(0xFFFFFFFFu, (v0 > 0.0f) || (v1 > 0.0f)) ? 1u : 0u;
+          slotp += adv;
+          nout += adv;
         }
         if (chunk_end % BL_CH == 0) {
           __syncwarp();
           if (lane == 0) {
-            S.hdr[g][slot] = BL_CH;
-            mbar_arrive(&S.full[g][slot]);
+            S.hdr[slot] = nout;
+            mbar_arrive(&S.full[slot]);
           }
         }
       }
@@ -285,37 +454,46 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint32_t *__restrict__ orde
     // terminator: the partial last chunk, or an empty extra chunk, carries the `last` flag
     {
       const uint32_t chunk = seq / BL_CH, rem = seq % BL_CH;
-      if ((chunk & 1u) == p) {
-        const uint32_t slot = chunk % BL_D;
-        if (rem == 0) mbar_wait(&S.empty[g][slot], ((chunk / BL_D) & 1u) ^ 1u);
+      if ((chunk & ppg_mask) == p) {
+        const uint32_t slot = (gl << d_log) + (chunk & d_mask);
+        if (rem == 0) {
+          mbar_wait<SPLAT_SPIN_PRODUCER>(&S.empty[slot], ((chunk >> d_log) & 1u) ^ 1u);
+          nout = 0;
+        }
         __syncwarp();
         if (lane == 0) {
-          S.hdr[g][slot] = rem | 0x100u;
-          mbar_arrive(&S.full[g][slot]);
+          S.hdr[slot] = nout | 0x100u;
+          mbar_arrive(&S.full[slot]);
         }
       }
     }
   } else {
     // ============================== CONSUMERS ==============================
-    const uint32_t g = w - BL_PRODUCER_THREADS / 32;
+    const uint32_t gl = w - BL_PRODUCER_THREADS / 32;
+    if (gl >= ng) return;   // split units: the spare consumer warps have nothing to do
+    const uint32_t g = g0 + gl;
     const uint32_t px = tx0 + 8u * (g & 1u) + (lane & 7u);
-    const uint32_t py = ty0 + 4u * (g >> 1) + (lane >> 3);
-    const bool inside = px < P.W && py < P.row1;
-    uint32_t *pix = fb_rows + (size_t)(py - P.row0) * P.W + px;
-    uint32_t old = 0;
-    if (inside) old = *pix;
-    float cr = div255((float)((old >> 16) & 0xFFu));
-    float cg = div255((float)((old >> 8) & 0xFFu));
-    float cb = div255((float)(old & 0xFFu));
+    const uint32_t py0 = ty0 + 8u * (g >> 1) + (lane >> 3), py1 = py0 + 4u;
+    const bool inside0 = px < P.W && py0 < P.row1, inside1 = px < P.W && py1 < P.row1;
+    uint32_t *pix0 = fb_rows + (size_t)(py0 - P.row0) * P.W + px;
+    uint32_t *pix1 = pix0 + (size_t)4u * P.W;
+    uint32_t old0 = 0, old1 = 0;
+    if (inside0) old0 = *pix0;
+    if (inside1) old1 = *pix1;
+    f32x2 cr = pk(div255((float)((old0 >> 16) & 0xFFu)), div255((float)((old1 >> 16) & 0xFFu)));
+    f32x2 cg = pk(div255((float)((old0 >> 8) & 0xFFu)), div255((float)((old1 >> 8) & 0xFFu)));
+    f32x2 cb = pk(div255((float)(old0 & 0xFFu)), div255((float)(old1 & 0xFFu)));
     // E7 (alpha byte).  blend() stores the CURRENT fragment's alpha, and euc calls it for every
     // covered pixel, so the byte a pixel ends up with belongs to the LAST entry of the list
     // whose 3-sigma rectangle covers it -- 0 if that fragment was zero.  That entry is found
     // here by walking the list backwards (typically a few dozen entries) while the producers
     // fill the ring; the main loop then only has to handle entries that change RGB.
-    const float sx = (float)px + P.sample_off, sy = (float)py + P.sample_off;
-    uint32_t last_g = 0xFFFFFFFFu;
-    bool found = !inside;
-    for (uint32_t end = range.y; end > range.x && __any_sync(0xFFFFFFFFu, !found); end -= min(32u, end - range.x)) {
+    const float sx = (float)px + P.sample_off;
+    const float sy0 = (float)py0 + P.sample_off, sy1 = (float)py1 + P.sample_off;
+    uint32_t last0 = 0xFFFFFFFFu, last1 = 0xFFFFFFFFu;
+    bool found0 = !inside0, found1 = !inside1;
+    for (uint32_t end = range.y; end > range.x && __any_sync(0xFFFFFFFFu, !(found0 && found1));
+         end -= min(32u, end - range.x)) {
       const uint32_t cntb = min(32u, end - range.x);
       uint32_t gi = 0;
       float ecx = 0.f, ecy = 0.f, ehx = -1.f, ehy = -1.f;
@@ -329,52 +507,50 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint32_t *__restrict__ orde
         const float kx = __shfl_sync(0xFFFFFFFFu, ecx, k), ky = __shfl_sync(0xFFFFFFFFu, ecy, k);
         const float khx = __shfl_sync(0xFFFFFFFFu, ehx, k), khy = __shfl_sync(0xFFFFFFFFu, ehy, k);
         const uint32_t kg = __shfl_sync(0xFFFFFFFFu, gi, k);
-        if (!found && fabsf(sx - kx) <= khx && fabsf(sy - ky) <= khy) { found = true; last_g = kg; }
-        if (!__any_sync(0xFFFFFFFFu, !found)) break;
+        const bool cx_in = fabsf(sx - kx) <= khx;
+        if (!found0 && cx_in && fabsf(sy0 - ky) <= khy) { found0 = true; last0 = kg; }
+        if (!found1 && cx_in && fabsf(sy1 - ky) <= khy) { found1 = true; last1 = kg; }
+        if (!__any_sync(0xFFFFFFFFu, !(found0 && found1))) break;
       }
     }
 
     for (uint32_t chunk = 0;; ++chunk) {
-      const uint32_t slot = chunk % BL_D;
-      mbar_wait(&S.full[g][slot], (chunk / BL_D) & 1u);
-      const uint32_t h = S.hdr[g][slot];
+      const uint32_t slot = (gl << d_log) + (chunk & d_mask);
+      mbar_wait<SPLAT_SPIN_CONSUMER>(&S.full[slot], (chunk >> d_log) & 1u);
+      const uint32_t h = S.hdr[slot];
       const uint32_t n = h & 0xFFu;
-      for (uint32_t e = 0; e < n; ++e) {
-        const float *slotp = &S.ring[g][slot][e][0];
-        const float al = slotp[lane];
-        if (__any_sync(0xFFFFFFFFu, al > 0.0f)) {
-          const float4 col = *reinterpret_cast<const float4 *>(slotp + 32);
-          if (al > 0.0f) {
-            const float om = __fsub_rn(1.0f, al);
-            cr = blend_channel(cr, om, __fmul_rn(al, col.x));
-            cg = blend_channel(cg, om, __fmul_rn(al, col.y));
-            cb = blend_channel(cb, om, __fmul_rn(al, col.z));
-          }
-        }
+      const RingEntry *ep = &S.ring[slot][0];
+      for (uint32_t e = 0; e < n; ++e, ++ep) {
+        const float2 al = ep->al[lane];
+        const float4 col = ep->col;
+        const f32x2 al2 = pk(al.x, al.y);
+        const f32x2 om = sub2(pk1(1.0f), al2);
+        // alpha == 0 is a natural no-op: out = 1*c + 0 and (x/255)*255 truncates back to x
+        cr = blend_channel2(cr, om, al2, col.x, NZ);
+        cg = blend_channel2(cg, om, al2, col.y, NZ);
+        cb = blend_channel2(cb, om, al2, col.z, NZ);
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&S.empty[g][slot]);
+      if (lane == 0) mbar_arrive(&S.empty[slot]);
       if (h & 0x100u) break;
     }
 
-    if (inside && last_g != 0xFFFFFFFFu) {
+    float r0, r1, g0, g1, b0, b1;
+    upk(cr, r0, r1); upk(cg, g0, g1); upk(cb, b0, b1);
+    if (inside0 && last0 != 0xFFFFFFFFu) {
       // fragment() of the last covering entry for this pixel (pipelines.rs:127-145)
-      const float4 *rp = reinterpret_cast<const float4 *>(recs + last_g);
-      const float4 a = __ldg(rp), b = __ldg(rp + 1);
-      const float dx = sx - a.x, dy = sy - a.y;
-      const float q1 = __fmul_rn(__fmul_rn(a.z, dx), dx);
-      const float q2 = __fmul_rn(__fmul_rn(b.x, dy), dy);
-      const float q3 = __fmul_rn(__fmul_rn(a.w, dx), dy);
-      const float power = __fsub_rn(__fmul_rn(-0.5f, __fadd_rn(q1, q2)), q3);
-      float last_alpha = 0.0f;
-      if (!(power > 0.0f)) {
-        const float ex = (power >= -87.0f) ? expf_pinned(power) : 0.0f;   // splat_expf flushes below -87
-        const float t = fminf(0.99f, __fmul_rn(b.y, ex));
-        if (!(t < (1.0f / 255.0f))) last_alpha = t;
-      }
-      const uint32_t r = (uint32_t)__fmul_rn(cr, 255.0f), gg = (uint32_t)__fmul_rn(cg, 255.0f);
-      const uint32_t bl = (uint32_t)__fmul_rn(cb, 255.0f), av = (uint32_t)__fmul_rn(last_alpha, 255.0f);
-      *pix = bl | (gg << 8) | (r << 16) | (av << 24);
+      const float4 *rp = reinterpret_cast<const float4 *>(recs + last0);
+      const float la = fragment_alpha(sx, sy0, __ldg(rp), __ldg(rp + 1));
+      const uint32_t r = (uint32_t)__fmul_rn(r0, 255.0f), gg = (uint32_t)__fmul_rn(g0, 255.0f);
+      const uint32_t bl = (uint32_t)__fmul_rn(b0, 255.0f), av = (uint32_t)__fmul_rn(la, 255.0f);
+      *pix0 = bl | (gg << 8) | (r << 16) | (av << 24);
+    }
+    if (inside1 && last1 != 0xFFFFFFFFu) {
+      const float4 *rp = reinterpret_cast<const float4 *>(recs + last1);
+      const float la = fragment_alpha(sx, sy1, __ldg(rp), __ldg(rp + 1));
+      const uint32_t r = (uint32_t)__fmul_rn(r1, 255.0f), gg = (uint32_t)__fmul_rn(g1, 255.0f);
+      const uint32_t bl = (uint32_t)__fmul_rn(b1, 255.0f), av = (uint32_t)__fmul_rn(la, 255.0f);
+      *pix1 = bl | (gg << 8) | (r << 16) | (av << 24);
     }
   }
 }

@@ -31,6 +31,7 @@ struct FrameParams {
   uint32_t tile_y0;    // first tile row of the stripe
   uint32_t tiles_y;    // tile rows in the stripe
   uint32_t n;          // Gaussians
+  unsigned long long nz2;  // (-0.0f, -0.0f): run-time addend that keeps packed products unfused (blend.cuh)
 };
 
 // Splat record produced by project_kernel and consumed by blend_kernel: 3 x float4 = 48 B.

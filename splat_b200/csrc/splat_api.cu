@@ -47,7 +47,8 @@ struct splat_ctx {
   uint64_t inst_cap = 0;
   uint32_t *ikeys[2] = {nullptr, nullptr}, *ivals[2] = {nullptr, nullptr};
   uint2 *ranges = nullptr; size_t ranges_cap = 0;
-  uint32_t *tile_order = nullptr;
+  uint2 *units = nullptr;          // blend work units, heaviest first (up to 4 per tile)
+  uint32_t *n_units = nullptr;
   FrameStatus *d_status = nullptr, *h_status = nullptr;
   uint32_t *d_fb = nullptr; size_t fb_cap = 0;
 
@@ -187,6 +188,7 @@ int make_params(splat_ctx *c, const splat_camera *cam, uint32_t W, uint32_t H, u
   P->tile_y0 = row0 / TILE;
   P->tiles_y = cdiv(row1, TILE) - P->tile_y0;
   P->n = c->n;
+  P->nz2 = 0x8000000080000000ull;
   return SPLAT_OK;
 }
 
@@ -235,9 +237,9 @@ int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cuda
   const uint32_t T = P.tiles_x * P.tiles_y;
   if (T > c->ranges_cap) {
     dev_free(c->ranges);
-    dev_free(c->tile_order);
+    dev_free(c->units);
     CU(dev_alloc(&c->ranges, T));
-    CU(dev_alloc(&c->tile_order, T));
+    CU(dev_alloc(&c->units, (size_t)4 * T));
     c->ranges_cap = T;
   }
   int icur = 0;
@@ -252,13 +254,13 @@ int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cuda
   CU(cudaMemsetAsync(c->ranges, 0, (size_t)T * sizeof(uint2), s));
   if (I > 0) {
     tile_ranges_kernel<<<cdiv(I, 256), 256, 0, s>>>(c->ikeys[icur], (uint32_t)I, c->ranges);
-    tile_order_kernel<<<1, 1024, 0, s>>>(c->ranges, T, c->tile_order);   // heaviest tiles first
+    unit_order_kernel<<<1, 1024, 0, s>>>(c->ranges, T, c->units, c->n_units, &c->d_status->n_instances);   // heaviest first
     c->launches += 2;
   }
   CU(cudaEventRecord(c->ev[EV_RANGES], s));
   if (wait_ev) CU(cudaStreamWaitEvent(s, wait_ev, 0));
   if (I > 0) {
-    blend_kernel<<<2 * T, BL_THREADS, 0, s>>>(c->ranges, c->tile_order, c->ivals[icur], c->recs, fb_rows_dev, P);
+    blend_kernel<<<4 * T, BL_THREADS, BL_SMEM_BYTES, s>>>(c->ranges, c->units, c->n_units, c->ivals[icur], c->recs, fb_rows_dev, P);
     c->launches += 1;
   }
   CU(cudaEventRecord(c->ev[EV_BLEND], s));
@@ -305,7 +307,10 @@ int splat_create(splat_ctx **out, const splat_config *cfg) {
     if (cudaEventCreate(&c->ev[i]) != cudaSuccess) return bail(SPLAT_ERR_CUDA);
   if (cudaEventCreateWithFlags(&c->status_ev, cudaEventDisableTiming) != cudaSuccess) return bail(SPLAT_ERR_CUDA);
   if (cudaEventCreateWithFlags(&c->h2d_done, cudaEventDisableTiming) != cudaSuccess) return bail(SPLAT_ERR_CUDA);
+  if (cudaFuncSetAttribute(blend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BL_SMEM_BYTES) != cudaSuccess)
+    return bail(SPLAT_ERR_CUDA);
   if (dev_alloc(&c->d_status, 1) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
+  if (dev_alloc(&c->n_units, 1) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
   if (cudaMallocHost(reinterpret_cast<void **>(&c->h_status), sizeof(FrameStatus)) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
   *out = c;
   return SPLAT_OK;
@@ -316,7 +321,7 @@ void splat_destroy(splat_ctx *c) {
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_scene(c);
-  dev_free(c->hist); dev_free(c->partial); dev_free(c->ranges); dev_free(c->tile_order); dev_free(c->d_status); dev_free(c->d_fb);
+  dev_free(c->hist); dev_free(c->partial); dev_free(c->ranges); dev_free(c->units); dev_free(c->n_units); dev_free(c->d_status); dev_free(c->d_fb);
   for (int k = 0; k < 2; ++k) { dev_free(c->ikeys[k]); dev_free(c->ivals[k]); }
   if (c->h_status) cudaFreeHost(c->h_status);
   for (int i = 0; i < EV_COUNT_; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
