@@ -40,6 +40,12 @@ enum {
   SPLAT_ERR_STATE = -5        /* render before upload                                           */
 };
 
+/* blend_mode values.  Only SPLAT_BLEND_REFERENCE reproduces the reference's pixels
+ * (pipelines.rs:147-168: u8 truncation after every Gaussian, far -> near). */
+enum {
+  SPLAT_BLEND_REFERENCE = 0
+};
+
 /* Behaviour switches.  lowpass selects which reference pipeline is reproduced; the three
  * euc-semantics switches mirror the assumptions E1/E3 of SURVEY.md section 8c and must match
  * the oracle's orc_config for parity. */
@@ -51,6 +57,8 @@ typedef struct {
   float    sample_offset;  /* pixel sample point (x+off, y+off); 0.5                             */
   uint32_t tile;           /* screen tile edge in pixels; only 16 is built                       */
   uint64_t max_instances;  /* initial capacity of the tile-instance buffers (0 = auto, grows)    */
+  int32_t  blend_mode;     /* SPLAT_BLEND_*: 0 = the reference's quantised far->near blend (parity) */
+  int32_t  reserved;       /* must be 0                                                          */
 } splat_config;
 
 /* What the kernels need from `Camera` (camera.rs:4-19): the two matrices exactly as nalgebra
@@ -139,6 +147,11 @@ int splat_debug_project(splat_ctx *ctx, const splat_camera *cam, uint32_t W, uin
                         float *records12, uint32_t *depth_keys, uint32_t *tile_rects4);
 int splat_debug_read_order(splat_ctx *ctx, uint32_t *order, uint64_t cap, uint64_t *n_visible);
 int splat_debug_sort_pairs(splat_ctx *ctx, uint32_t *keys, uint32_t *vals, uint64_t n, int bits);
+/* Work counters of the blend kernel accumulated since the last reset (instrumented builds,
+ * -DSPLAT_STATS, only; SPLAT_ERR_UNSUPPORTED otherwise): out8[0] group-entries evaluated,
+ * [1] group-entries that changed a pixel, [2] (pixel, Gaussian) pairs with alpha > 0,
+ * [3] tile-list entries staged, [4] candidate pairs, [5] pixel-pair lanes with alpha > 0. */
+int splat_debug_blend_stats(splat_ctx *ctx, uint64_t *out8, int reset);
 
 #ifdef __cplusplus
 }

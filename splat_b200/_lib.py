@@ -21,13 +21,13 @@ EXPORTS = ["splat_abi_version", "splat_config_default", "splat_create", "splat_d
            "splat_last_error", "splat_upload_soa", "splat_upload_aos", "splat_render",
            "splat_render_rows", "splat_render_device", "splat_get_timings", "splat_pin_host",
            "splat_unpin_host", "splat_debug_project", "splat_debug_read_order",
-           "splat_debug_sort_pairs"]
+           "splat_debug_sort_pairs", "splat_debug_blend_stats"]
 
 
 class SplatConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("lowpass", C.c_float), ("y_down", C.c_int32),
                 ("zclip_mode", C.c_int32), ("sample_offset", C.c_float), ("tile", C.c_uint32),
-                ("max_instances", C.c_uint64)]
+                ("max_instances", C.c_uint64), ("blend_mode", C.c_int32), ("reserved", C.c_int32)]
 
 
 class SplatCamera(C.Structure):
@@ -85,6 +85,7 @@ def load():
     L.splat_debug_project.argtypes = [vp, C.POINTER(SplatCamera), C.c_uint32, C.c_uint32, vp, vp, vp]
     L.splat_debug_read_order.argtypes = [vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.splat_debug_sort_pairs.argtypes = [vp, vp, vp, C.c_uint64, C.c_int]
+    L.splat_debug_blend_stats.argtypes = [vp, vp, C.c_int]
     for name in EXPORTS:
         getattr(L, name)  # AttributeError if the .so does not export it
     _lib = L
@@ -183,6 +184,11 @@ class Context:
         nv = C.c_uint64()
         self._check(self.L.splat_debug_read_order(self.h, order.ctypes.data, len(order), C.byref(nv)))
         return order[: nv.value].copy()
+
+    def debug_blend_stats(self, reset=True) -> np.ndarray:
+        out = np.zeros(8, np.uint64)
+        self._check(self.L.splat_debug_blend_stats(self.h, out.ctypes.data, int(reset)))
+        return out
 
     def debug_sort_pairs(self, keys: np.ndarray, vals: np.ndarray, bits=32):
         assert keys.dtype == np.uint32 and vals.dtype == np.uint32

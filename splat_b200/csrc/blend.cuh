@@ -10,7 +10,7 @@
 //   old = byte / 255           (IEEE division; here a 2-op fmaf form, exact for all 256 bytes)
 //   out = (1-a)*old + a*new    (two products, one add, no FMA)
 //   byte' = trunc_sat(out*255) (round-toward-zero add of 2^23)
-// exp() is the pinned "splat_expf v1" sequence shared with the oracle (oracle/splat_oracle.c).
+// exp() is the pinned "splat_expf v1" operation sequence, restated independently by the CPU checker.
 //
 // The kernel is bound by the FP32 pipe (about 45 IEEE operations per pixel-Gaussian pair, 3.8e9
 // contributing pairs per 1080p frame of the 6.1M scene), not by HBM, so the design minimises
@@ -238,6 +238,14 @@ unit_order_kernel(const uint2 *__restrict__ ranges, uint32_t T, uint2 *__restric
 }
 
 // ---------------------------------------------------------------- K5
+#ifdef SPLAT_STATS
+// instrumented build only (tools/run_stats.sh): work counters of the blend kernel
+//  [0] group-entries evaluated by producers  [1] group-entries handed to consumers
+//  [2] pixels with alpha > 0                 [3] list entries staged (per unit)
+//  [4] candidate pixels (rect + power tests) [5] lanes (pixel pairs) with alpha > 0
+__device__ unsigned long long g_blend_stats[8];
+#define STAT_ADD(i, v) atomicAdd(&g_blend_stats[i], (unsigned long long)(v))
+#endif
 struct RingEntry {
   float2 al[32];   // per lane: alpha of pixel (x, y) and of pixel (x, y+4); 0 = no change
   float4 col;      // r, g, b (+ the power threshold, unused by the consumer)
@@ -313,6 +321,9 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t seq = 0;    // list entries of this team handed out so far (both producers count alike)
     uint32_t nout = 0;   // entries written into the chunk this producer is filling
+#ifdef SPLAT_STATS
+    uint32_t st_eval = 0, st_out = 0, st_pix = 0, st_cand = 0, st_lanes = 0;
+#endif
 
     for (uint32_t base = range.x; base < range.y; base += BL_BATCH) {
       const uint32_t nb = min((uint32_t)BL_BATCH, range.y - base);
@@ -438,6 +449,11 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
           if (lane == 0) slotp->col = c;
           // entries that change no pixel of the group are overwritten by the next one
           const uint32_t adv = __any_sync(0xFFFFFFFFu, (v0 > 0.0f) || (v1 > 0.0f)) ? 1u : 0u;
+#ifdef SPLAT_STATS
+          st_eval += 1; st_out += adv;
+          st_pix += (v0 > 0.0f) + (v1 > 0.0f); st_cand += (uint32_t)cand0 + (uint32_t)cand1;
+          st_lanes += ((v0 > 0.0f) || (v1 > 0.0f)) ? 1u : 0u;
+#endif
           slotp += adv;
           nout += adv;
         }
@@ -450,7 +466,19 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
         }
       }
       seq = s_end;
+#ifdef SPLAT_STATS
+      if (tid == 0) STAT_ADD(3, nb);
+#endif
     }
+#ifdef SPLAT_STATS
+    {
+      uint32_t a = st_pix, b = st_cand, c = st_lanes;
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xFFFFFFFFu, a, o); b += __shfl_xor_sync(0xFFFFFFFFu, b, o); c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+      }
+      if (lane == 0) { STAT_ADD(0, st_eval); STAT_ADD(1, st_out); STAT_ADD(2, a); STAT_ADD(4, b); STAT_ADD(5, c); }
+    }
+#endif
     // terminator: the partial last chunk, or an empty extra chunk, carries the `last` flag
     {
       const uint32_t chunk = seq / BL_CH, rem = seq % BL_CH;

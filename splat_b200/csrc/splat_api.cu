@@ -289,6 +289,8 @@ void splat_config_default(splat_config *cfg) {
   cfg->sample_offset = 0.5f;
   cfg->tile = TILE;
   cfg->max_instances = 0;
+  cfg->blend_mode = SPLAT_BLEND_REFERENCE;
+  cfg->reserved = 0;
 }
 
 int splat_create(splat_ctx **out, const splat_config *cfg) {
@@ -299,6 +301,7 @@ int splat_create(splat_ctx **out, const splat_config *cfg) {
   if (cfg) c->cfg = *cfg; else splat_config_default(&c->cfg);
   auto bail = [&](int code) { splat_destroy(c); return code; };
   if (c->cfg.tile != (uint32_t)TILE) return bail(SPLAT_ERR_UNSUPPORTED);
+  if (c->cfg.blend_mode != SPLAT_BLEND_REFERENCE) return bail(SPLAT_ERR_UNSUPPORTED);
   if (!(c->cfg.lowpass >= 0.0f) || !std::isfinite(c->cfg.sample_offset)) return bail(SPLAT_ERR_INVALID);
   if (cudaSetDevice(c->cfg.device) != cudaSuccess) return bail(SPLAT_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(SPLAT_ERR_CUDA);
@@ -505,6 +508,23 @@ int splat_debug_sort_pairs(splat_ctx *c, uint32_t *keys, uint32_t *vals, uint64_
   for (int i = 0; i < 2; ++i) { dev_free(k[i]); dev_free(v[i]); }
   c->n = saved_n;
   return rc;
+}
+
+int splat_debug_blend_stats(splat_ctx *c, uint64_t *out8, int reset) {
+  if (!c || !out8) return SPLAT_ERR_INVALID;
+#ifdef SPLAT_STATS
+  CU(cudaSetDevice(c->cfg.device));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpyFromSymbol(out8, g_blend_stats, 8 * sizeof(uint64_t)));
+  if (reset) {
+    const uint64_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    CU(cudaMemcpyToSymbol(g_blend_stats, z, sizeof(z)));
+  }
+  return SPLAT_OK;
+#else
+  (void)reset;
+  return fail(c, SPLAT_ERR_UNSUPPORTED, "library built without -DSPLAT_STATS");
+#endif
 }
 
 int splat_pin_host(void *p, uint64_t bytes) {

@@ -1,0 +1,14 @@
+#!/bin/bash
+# usage (under gpurun): bash tools/gpu_round.sh <tag>   -- parity tests, bench, launch list, one full ncu capture of blend
+tag=${1:-rX}
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/pytest_$tag.txt
+python bench.py --steps 20 --warmup 3 > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.log; tail -3 gpurun_out/bench_$tag.log; cat gpurun_out/bench_$tag.json
+if [ -f splat_b200/libsplat_b200_stats.so ]; then
+  SPLAT_B200_LIB=$PWD/splat_b200/libsplat_b200_stats.so python tools/blend_stats.py 2>/dev/null | tee gpurun_out/stats_$tag.jsonl
+fi
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$tag.csv \
+    python bench.py --steps 6 --warmup 3 --no-cpu > gpurun_out/ncu_bench_$tag.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:blend_kernel -s 4 -c 1 -o gpurun_out/blend_$tag -f \
+    python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/ncu_full_$tag.log 2>&1
+ls -la gpurun_out | tail -12
