@@ -131,6 +131,12 @@ int splat_render_device(splat_ctx *ctx, const splat_camera *cam, void *fb_rows_d
 /* Blocks until the last enqueued render finished, then reports its stage times. */
 int splat_get_timings(splat_ctx *ctx, splat_timings *out);
 
+/* Tile-list lengths of the last completed render: per_tile[ty * tiles_x + tx] = number of
+ * (tile, Gaussian) instances of that tile of the rendered stripe (tiles_x = ceil(W/16)).  The
+ * multi-GPU driver sums them per tile row to place stripe boundaries.  Writes
+ * min(cap, n_tiles) entries and returns the stripe's tile count in *n_tiles. */
+int splat_get_tile_loads(splat_ctx *ctx, uint32_t *per_tile, uint64_t cap, uint64_t *n_tiles);
+
 /* Pin / unpin a caller-owned host buffer (cudaHostRegister) so that the framebuffer copies of
  * splat_render run at full PCIe rate; e.g. the Rust shim pins `color.raw_mut()` once. */
 int splat_pin_host(void *p, uint64_t bytes);

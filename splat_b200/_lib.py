@@ -19,7 +19,7 @@ ERRORS = {-1: "SPLAT_ERR_INVALID", -2: "SPLAT_ERR_CUDA", -3: "SPLAT_ERR_NOMEM",
 # every symbol include/splat.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = ["splat_abi_version", "splat_config_default", "splat_create", "splat_destroy",
            "splat_last_error", "splat_upload_soa", "splat_upload_aos", "splat_render",
-           "splat_render_rows", "splat_render_device", "splat_get_timings", "splat_pin_host",
+           "splat_render_rows", "splat_render_device", "splat_get_timings", "splat_get_tile_loads", "splat_pin_host",
            "splat_unpin_host", "splat_debug_project", "splat_debug_read_order",
            "splat_debug_sort_pairs", "splat_debug_blend_stats"]
 
@@ -80,6 +80,7 @@ def load():
     L.splat_render_rows.argtypes = [vp, C.POINTER(SplatCamera), vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     L.splat_render_device.argtypes = [vp, C.POINTER(SplatCamera), vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp]
     L.splat_get_timings.argtypes = [vp, C.POINTER(SplatTimings)]
+    L.splat_get_tile_loads.argtypes = [vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.splat_pin_host.argtypes = [vp, C.c_uint64]
     L.splat_unpin_host.argtypes = [vp]
     L.splat_debug_project.argtypes = [vp, C.POINTER(SplatCamera), C.c_uint32, C.c_uint32, vp, vp, vp]
@@ -169,6 +170,14 @@ class Context:
         t = SplatTimings()
         self._check(self.L.splat_get_timings(self.h, C.byref(t)))
         return t.as_dict()
+
+    def tile_loads(self, tiles_x: int) -> np.ndarray:
+        """(tile_rows, tiles_x) instance counts of the last render's stripe."""
+        nt = C.c_uint64()
+        t = self.timings()
+        out = np.zeros(max(int(t["n_tiles"]), 1), np.uint32)
+        self._check(self.L.splat_get_tile_loads(self.h, out.ctypes.data, len(out), C.byref(nt)))
+        return out[: nt.value].reshape(-1, tiles_x)
 
     def debug_project(self, cam: SplatCamera):
         H, W = int(cam.h), int(cam.w)

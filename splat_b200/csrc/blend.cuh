@@ -34,6 +34,20 @@
 //     producer warps (one entry per thread), which also compact, per group, the indices of
 //     the entries whose 3-sigma rectangle and alpha >= 1/255 ellipse can touch the group.
 //
+// Exact early termination.  The recurrence cannot be cut short by a transmittance threshold, but
+// it has a property that gives the same saving without changing a single bit: for a fixed entry
+// (alpha, colour) the map old byte -> new byte is monotone non-decreasing (every step -- the two
+// correctly rounded products, the rounded sum, the saturation, the rounded x255, the truncation,
+// the correctly rounded /255 -- is monotone in `old`), and so is any composition of such maps.
+// Hence if a run of entries sends BOTH byte 0 and byte 255 to the same byte v, it sends every
+// byte to v: the pixel's final value is independent of everything before that run and of the
+// framebuffer contents.  The kernel therefore composites only a SUFFIX of the tile list, carrying
+// two states per pixel (started at 0 and at 255) until they coincide for all pixels of the group
+// and one state afterwards; if some pixel has not converged when the list ends the attempt is
+// repeated with a 4x longer suffix, and an attempt that reaches the head of the list starts from
+// the real framebuffer bytes (the plain algorithm).  On the 6.1M-Gaussian bench scene a pixel is
+// covered by ~1,800 contributing entries of which the last ~100 decide its value.
+//
 // ptxas contracts mul.f32x2 + add.f32x2 into FFMA2 even under --fmad=false (seen in SASS), which
 // would change roundings.  Every packed product that feeds an addition is therefore written as
 // fma(a, b, nz) with nz = (-0.0, -0.0) read from the kernel parameters at run time: a*b + (-0)
@@ -49,6 +63,15 @@ constexpr int BL_THREADS = BL_PRODUCER_THREADS + 32 * BL_GROUPS;   // + one cons
 constexpr int BL_BATCH = 256;                      // list entries staged per round
 constexpr int BL_CH = 8;                           // list entries per ring chunk
 constexpr int BL_SLOTS = 16;                       // ring chunk slots per CTA, split among the unit's groups
+#ifndef SPLAT_SUFFIX0
+#define SPLAT_SUFFIX0 512
+#endif
+#ifndef SPLAT_SUFFIX_GROWTH
+#define SPLAT_SUFFIX_GROWTH 4
+#endif
+constexpr uint32_t BL_SUFFIX0 = SPLAT_SUFFIX0;              // list entries composited by the first suffix attempt
+constexpr uint32_t BL_SUFFIX_GROWTH = SPLAT_SUFFIX_GROWTH;  // growth factor per failed attempt
+constexpr uint32_t BL_SUFFIX_MIN_LEN = 3 * BL_SUFFIX0 / 2;  // shorter lists are composited whole, straight away
 
 // ---------------------------------------------------------------- packed f32x2 helpers
 typedef unsigned long long f32x2;   // two IEEE binary32 values in one 64-bit register pair
@@ -154,6 +177,15 @@ SPLAT_DEVINL f32x2 blend_channel2(f32x2 c_old, f32x2 om, f32x2 al, float col, f3
 }
 
 // ---------------------------------------------------------------- mbarrier / named barrier
+#ifndef SPLAT_SLEEP_NS
+#define SPLAT_SLEEP_NS 64
+#endif
+#ifndef SPLAT_SLEEP_NS_CONSUMER
+#define SPLAT_SLEEP_NS_CONSUMER 32
+#endif
+#ifndef SPLAT_MAX_PPG_LOG
+#define SPLAT_MAX_PPG_LOG 3   // at most 2^this producer warps evaluate for one group; the rest only stage
+#endif
 SPLAT_DEVINL uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 SPLAT_DEVINL void mbar_init(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -162,11 +194,14 @@ SPLAT_DEVINL void mbar_arrive(uint64_t *bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.release.cta.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar))
                : "memory");
 }
-// Blocking wait.  SPIN = false: try_wait with a suspend-time hint (the warp sleeps in hardware
-// and stops taking issue slots); SPIN = true: test_wait polling (lowest wake-up latency).
-template <bool SPIN>
+// Blocking wait on an mbarrier phase.  MODE 0: test_wait polling (lowest wake-up latency, but a
+// polling warp keeps taking issue slots from the warps that do the work).  MODE 1: try_wait with
+// a suspend-time hint (measured on B200: the suspended warp is woken by unrelated barrier
+// traffic and re-polls ~10^9 times per frame, 21% of all issued instructions in r1d).
+// MODE 2: test_wait, then nanosleep with a short back-off -- a sleeping warp issues nothing.
+template <int MODE>
 SPLAT_DEVINL void mbar_wait(uint64_t *bar, uint32_t parity) {
-  if (SPIN) {
+  if (MODE == 0) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
@@ -176,7 +211,7 @@ SPLAT_DEVINL void mbar_wait(uint64_t *bar, uint32_t parity) {
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
-  } else {
+  } else if (MODE == 1) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
@@ -186,14 +221,31 @@ SPLAT_DEVINL void mbar_wait(uint64_t *bar, uint32_t parity) {
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
         "r"(parity), "r"(0x989680u)
         : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "WAIT_%=:\n\t"
+        "nanosleep.u32 %2;\n\t"
+        "mbarrier.test_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity), "n"(MODE == 2 ? SPLAT_SLEEP_NS : SPLAT_SLEEP_NS_CONSUMER)
+        : "memory");
   }
 }
-#ifndef SPLAT_SPIN_CONSUMER
-#define SPLAT_SPIN_CONSUMER true
+#ifndef SPLAT_WAIT_CONSUMER
+#define SPLAT_WAIT_CONSUMER 0
 #endif
-#ifndef SPLAT_SPIN_PRODUCER
-#define SPLAT_SPIN_PRODUCER false
+#ifndef SPLAT_WAIT_PRODUCER
+#define SPLAT_WAIT_PRODUCER 2
 #endif
+SPLAT_DEVINL void mbar_inval(uint64_t *bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// all threads that take part in a unit (the 8 producer warps + its consumer warps)
+SPLAT_DEVINL void unit_sync(uint32_t nthreads) { asm volatile("bar.sync 2, %0;" ::"r"(nthreads) : "memory"); }
 SPLAT_DEVINL void producers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(BL_PRODUCER_THREADS) : "memory"); }
 
 // ---------------------------------------------------------------- heaviest-first unit order
@@ -257,6 +309,7 @@ struct BlendSmem {
   uint32_t hdr[BL_SLOTS];                                 // entries in the chunk | last << 8
   uint32_t wcount[BL_GROUPS][BL_PRODUCER_THREADS / 32];   // per staging warp, per group
   uint8_t list[BL_GROUPS][BL_BATCH];                      // compacted entry indices per group
+  uint32_t fail[BL_GROUPS];                               // per team: the suffix attempt did not converge
 };
 constexpr size_t BL_SMEM_BYTES = sizeof(BlendSmem);
 
@@ -294,16 +347,42 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
   const uint32_t tx0 = tile_x * TILE, ty0 = (P.tile_y0 + tile_y) * TILE;
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+  if (w >= BL_PRODUCER_THREADS / 32 + ng) return;   // split units: the spare consumer warps have nothing to do
+  const uint32_t nsync = BL_PRODUCER_THREADS + 32u * ng;   // threads that take part in this unit
+  const f32x2 NZ = P.nz2;
+  const uint32_t len = range.y - range.x;
+  uint32_t suffix = BL_SUFFIX0;
+
+  // ---- suffix attempts (see "Exact early termination" in the header) ----
+  // Attempt k composites only the last `suffix` list entries, starting every pixel from BOTH
+  // extreme states (byte 0 and byte 255).  Each entry's byte -> byte map is monotone, so once
+  // the two trajectories of a pixel coincide the result no longer depends on anything earlier
+  // in the list -- or on the framebuffer contents.  If some pixel has not converged when the
+  // list ends, the attempt is repeated with a 4x longer suffix; an attempt that reaches the
+  // head of the list starts from the real framebuffer bytes and is exact by construction.
+  uint32_t start = range.x;
+  bool exact = true;
+  // consumer state that survives the attempt loop
+  f32x2 cr = 0, cg = 0, cb = 0;
+  uint32_t last0 = 0xFFFFFFFFu, last1 = 0xFFFFFFFFu;
+  bool alpha_done = false;
+
+  for (;;) {
+  exact = (len <= BL_SUFFIX_MIN_LEN) || (suffix >= len);
+  start = exact ? range.x : range.y - suffix;
   if (tid < BL_SLOTS) {
     mbar_init(&S.full[tid], 1);
     mbar_init(&S.empty[tid], 1);
   }
-  __syncthreads();
-  const f32x2 NZ = P.nz2;
+  unit_sync(nsync);
 
   if (w < BL_PRODUCER_THREADS / 32) {
     // ============================== PRODUCERS ==============================
     const uint32_t gl = w >> ppg_log, p = w & ppg_mask, g = g0 + gl;   // local team, rank in team, group
+    // SPLAT_MAX_PPG_LOG < 3 lets the surplus producer warps of a split unit only stage (measured
+    // r1e: slower -- the heavy units are the critical path and want every producer they can get).
+    const uint32_t ev_mask = min(ppg_mask, (1u << SPLAT_MAX_PPG_LOG) - 1u);
+    const bool evaluates = p <= ev_mask;
     const uint32_t unit_mask = ((1u << ng) - 1u) << g0;
     const float sx = (float)(tx0 + 8u * (g & 1u) + (lane & 7u)) + P.sample_off;
     const float sy0 = (float)(ty0 + 8u * (g >> 1) + (lane >> 3)) + P.sample_off;
@@ -325,7 +404,7 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
     uint32_t st_eval = 0, st_out = 0, st_pix = 0, st_cand = 0, st_lanes = 0;
 #endif
 
-    for (uint32_t base = range.x; base < range.y; base += BL_BATCH) {
+    for (uint32_t base = start; base < range.y; base += BL_BATCH) {
       const uint32_t nb = min((uint32_t)BL_BATCH, range.y - base);
       producers_sync();   // previous batch no longer read by any producer
       uint32_t bits = 0;
@@ -404,15 +483,17 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
       }
       producers_sync();
 
-      uint32_t s = seq;
+      // chunks of BL_CH consecutive list entries of the team are dealt round-robin to its
+      // evaluating producers: chunk c belongs to producer (c & ev_mask)
       const uint32_t s_end = seq + n_mine;
-      while (s < s_end) {
-        const uint32_t chunk = s / BL_CH;
+      uint32_t chunk = seq / BL_CH;
+      chunk += (p - chunk) & ev_mask;                      // first chunk >= seq/BL_CH owned by p
+      for (; evaluates && chunk * BL_CH < s_end; chunk += ev_mask + 1u) {
+        uint32_t s = max(seq, chunk * BL_CH);
         const uint32_t chunk_end = min(s_end, (chunk + 1) * BL_CH);
-        if ((chunk & ppg_mask) != p) { s = chunk_end; continue; }
         const uint32_t slot = (gl << d_log) + (chunk & d_mask);
         if (s % BL_CH == 0) {
-          mbar_wait<SPLAT_SPIN_PRODUCER>(&S.empty[slot], ((chunk >> d_log) & 1u) ^ 1u);
+          mbar_wait<SPLAT_WAIT_PRODUCER>(&S.empty[slot], ((chunk >> d_log) & 1u) ^ 1u);
           nout = 0;
         }
         RingEntry *slotp = &S.ring[slot][nout];
@@ -482,10 +563,10 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
     // terminator: the partial last chunk, or an empty extra chunk, carries the `last` flag
     {
       const uint32_t chunk = seq / BL_CH, rem = seq % BL_CH;
-      if ((chunk & ppg_mask) == p) {
+      if (evaluates && (chunk & ev_mask) == p) {
         const uint32_t slot = (gl << d_log) + (chunk & d_mask);
         if (rem == 0) {
-          mbar_wait<SPLAT_SPIN_PRODUCER>(&S.empty[slot], ((chunk >> d_log) & 1u) ^ 1u);
+          mbar_wait<SPLAT_WAIT_PRODUCER>(&S.empty[slot], ((chunk >> d_log) & 1u) ^ 1u);
           nout = 0;
         }
         __syncwarp();
@@ -498,85 +579,145 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
   } else {
     // ============================== CONSUMERS ==============================
     const uint32_t gl = w - BL_PRODUCER_THREADS / 32;
-    if (gl >= ng) return;   // split units: the spare consumer warps have nothing to do
     const uint32_t g = g0 + gl;
     const uint32_t px = tx0 + 8u * (g & 1u) + (lane & 7u);
     const uint32_t py0 = ty0 + 8u * (g >> 1) + (lane >> 3), py1 = py0 + 4u;
     const bool inside0 = px < P.W && py0 < P.row1, inside1 = px < P.W && py1 < P.row1;
-    uint32_t *pix0 = fb_rows + (size_t)(py0 - P.row0) * P.W + px;
-    uint32_t *pix1 = pix0 + (size_t)4u * P.W;
-    uint32_t old0 = 0, old1 = 0;
-    if (inside0) old0 = *pix0;
-    if (inside1) old1 = *pix1;
-    f32x2 cr = pk(div255((float)((old0 >> 16) & 0xFFu)), div255((float)((old1 >> 16) & 0xFFu)));
-    f32x2 cg = pk(div255((float)((old0 >> 8) & 0xFFu)), div255((float)((old1 >> 8) & 0xFFu)));
-    f32x2 cb = pk(div255((float)(old0 & 0xFFu)), div255((float)(old1 & 0xFFu)));
-    // E7 (alpha byte).  blend() stores the CURRENT fragment's alpha, and euc calls it for every
-    // covered pixel, so the byte a pixel ends up with belongs to the LAST entry of the list
-    // whose 3-sigma rectangle covers it -- 0 if that fragment was zero.  That entry is found
-    // here by walking the list backwards (typically a few dozen entries) while the producers
-    // fill the ring; the main loop then only has to handle entries that change RGB.
     const float sx = (float)px + P.sample_off;
     const float sy0 = (float)py0 + P.sample_off, sy1 = (float)py1 + P.sample_off;
-    uint32_t last0 = 0xFFFFFFFFu, last1 = 0xFFFFFFFFu;
-    bool found0 = !inside0, found1 = !inside1;
-    for (uint32_t end = range.y; end > range.x && __any_sync(0xFFFFFFFFu, !(found0 && found1));
-         end -= min(32u, end - range.x)) {
-      const uint32_t cntb = min(32u, end - range.x);
-      uint32_t gi = 0;
-      float ecx = 0.f, ecy = 0.f, ehx = -1.f, ehy = -1.f;
-      if (lane < cntb) {
-        gi = __ldg(&inst_vals[end - 1u - lane]);
-        const float4 *rp = reinterpret_cast<const float4 *>(recs + gi);
-        const float4 a = __ldg(rp), b = __ldg(rp + 1);
-        ecx = a.x; ecy = a.y; ehx = b.z; ehy = b.w;
+    if (!alpha_done) {
+      // E7 (alpha byte).  blend() stores the CURRENT fragment's alpha, and euc calls it for every
+      // covered pixel, so the byte a pixel ends up with belongs to the LAST entry of the list
+      // whose 3-sigma rectangle covers it -- 0 if that fragment was zero.  That entry is found
+      // here by walking the list backwards (typically a few dozen entries) while the producers
+      // fill the ring; the main loop then only has to handle entries that change RGB.
+      alpha_done = true;
+      bool found0 = !inside0, found1 = !inside1;
+      for (uint32_t end = range.y; end > range.x && __any_sync(0xFFFFFFFFu, !(found0 && found1));
+           end -= min(32u, end - range.x)) {
+        const uint32_t cntb = min(32u, end - range.x);
+        uint32_t gi = 0;
+        float ecx = 0.f, ecy = 0.f, ehx = -1.f, ehy = -1.f;
+        if (lane < cntb) {
+          gi = __ldg(&inst_vals[end - 1u - lane]);
+          const float4 *rp = reinterpret_cast<const float4 *>(recs + gi);
+          const float4 a = __ldg(rp), b = __ldg(rp + 1);
+          ecx = a.x; ecy = a.y; ehx = b.z; ehy = b.w;
+        }
+        for (uint32_t k = 0; k < cntb; ++k) {
+          const float kx = __shfl_sync(0xFFFFFFFFu, ecx, k), ky = __shfl_sync(0xFFFFFFFFu, ecy, k);
+          const float khx = __shfl_sync(0xFFFFFFFFu, ehx, k), khy = __shfl_sync(0xFFFFFFFFu, ehy, k);
+          const uint32_t kg = __shfl_sync(0xFFFFFFFFu, gi, k);
+          const bool cx_in = fabsf(sx - kx) <= khx;
+          if (!found0 && cx_in && fabsf(sy0 - ky) <= khy) { found0 = true; last0 = kg; }
+          if (!found1 && cx_in && fabsf(sy1 - ky) <= khy) { found1 = true; last1 = kg; }
+          if (!__any_sync(0xFFFFFFFFu, !(found0 && found1))) break;
+        }
       }
-      for (uint32_t k = 0; k < cntb; ++k) {
-        const float kx = __shfl_sync(0xFFFFFFFFu, ecx, k), ky = __shfl_sync(0xFFFFFFFFu, ecy, k);
-        const float khx = __shfl_sync(0xFFFFFFFFu, ehx, k), khy = __shfl_sync(0xFFFFFFFFu, ehy, k);
-        const uint32_t kg = __shfl_sync(0xFFFFFFFFu, gi, k);
-        const bool cx_in = fabsf(sx - kx) <= khx;
-        if (!found0 && cx_in && fabsf(sy0 - ky) <= khy) { found0 = true; last0 = kg; }
-        if (!found1 && cx_in && fabsf(sy1 - ky) <= khy) { found1 = true; last1 = kg; }
-        if (!__any_sync(0xFFFFFFFFu, !(found0 && found1))) break;
-      }
+    }
+    // pixels whose value matters: inside the image and covered by at least one quad
+    const bool need0 = inside0 && last0 != 0xFFFFFFFFu, need1 = inside1 && last1 != 0xFFFFFFFFu;
+
+    // state: lo trajectory in cr/cg/cb, hi trajectory in hr/hg/hb (only while `dual`)
+    f32x2 hr, hg, hb;
+    bool dual = !exact;
+    if (exact) {
+      const uint32_t *pix0 = fb_rows + (size_t)(py0 - P.row0) * P.W + px;
+      uint32_t old0 = 0, old1 = 0;
+      if (inside0) old0 = *pix0;
+      if (inside1) old1 = *(pix0 + (size_t)4u * P.W);
+      cr = pk(div255((float)((old0 >> 16) & 0xFFu)), div255((float)((old1 >> 16) & 0xFFu)));
+      cg = pk(div255((float)((old0 >> 8) & 0xFFu)), div255((float)((old1 >> 8) & 0xFFu)));
+      cb = pk(div255((float)(old0 & 0xFFu)), div255((float)(old1 & 0xFFu)));
+      hr = cr; hg = cg; hb = cb;
+    } else {
+      cr = cg = cb = pk1(0.0f);            // byte 0
+      hr = hg = hb = pk1(1.0f);            // byte 255: div255(255) == 1
     }
 
     for (uint32_t chunk = 0;; ++chunk) {
       const uint32_t slot = (gl << d_log) + (chunk & d_mask);
-      mbar_wait<SPLAT_SPIN_CONSUMER>(&S.full[slot], (chunk >> d_log) & 1u);
+      mbar_wait<SPLAT_WAIT_CONSUMER>(&S.full[slot], (chunk >> d_log) & 1u);
       const uint32_t h = S.hdr[slot];
       const uint32_t n = h & 0xFFu;
       const RingEntry *ep = &S.ring[slot][0];
-      for (uint32_t e = 0; e < n; ++e, ++ep) {
-        const float2 al = ep->al[lane];
-        const float4 col = ep->col;
-        const f32x2 al2 = pk(al.x, al.y);
-        const f32x2 om = sub2(pk1(1.0f), al2);
-        // alpha == 0 is a natural no-op: out = 1*c + 0 and (x/255)*255 truncates back to x
-        cr = blend_channel2(cr, om, al2, col.x, NZ);
-        cg = blend_channel2(cg, om, al2, col.y, NZ);
-        cb = blend_channel2(cb, om, al2, col.z, NZ);
+      if (dual) {
+#pragma unroll 2
+        for (uint32_t e = 0; e < n; ++e, ++ep) {
+          const float2 al = ep->al[lane];
+          const float4 col = ep->col;
+          const f32x2 al2 = pk(al.x, al.y);
+          const f32x2 om = sub2(pk1(1.0f), al2);
+          cr = blend_channel2(cr, om, al2, col.x, NZ);
+          hr = blend_channel2(hr, om, al2, col.x, NZ);
+          cg = blend_channel2(cg, om, al2, col.y, NZ);
+          hg = blend_channel2(hg, om, al2, col.y, NZ);
+          cb = blend_channel2(cb, om, al2, col.z, NZ);
+          hb = blend_channel2(hb, om, al2, col.z, NZ);
+        }
+        float l0, l1, u0, u1;
+        bool m0 = true, m1 = true;
+        upk(cr, l0, l1); upk(hr, u0, u1); m0 = m0 && (l0 == u0); m1 = m1 && (l1 == u1);
+        upk(cg, l0, l1); upk(hg, u0, u1); m0 = m0 && (l0 == u0); m1 = m1 && (l1 == u1);
+        upk(cb, l0, l1); upk(hb, u0, u1); m0 = m0 && (l0 == u0); m1 = m1 && (l1 == u1);
+        if (__all_sync(0xFFFFFFFFu, (m0 || !need0) && (m1 || !need1))) dual = false;
+      } else {
+        for (uint32_t e = 0; e < n; ++e, ++ep) {
+          const float2 al = ep->al[lane];
+          const float4 col = ep->col;
+          const f32x2 al2 = pk(al.x, al.y);
+          const f32x2 om = sub2(pk1(1.0f), al2);
+          // alpha == 0 is a natural no-op: out = 1*c + 0 and (x/255)*255 truncates back to x
+          cr = blend_channel2(cr, om, al2, col.x, NZ);
+          cg = blend_channel2(cg, om, al2, col.y, NZ);
+          cb = blend_channel2(cb, om, al2, col.z, NZ);
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.empty[slot]);
       if (h & 0x100u) break;
     }
+    if (lane == 0) S.fail[gl] = dual ? 1u : 0u;
+#ifdef SPLAT_STATS
+    if (lane == 0) { STAT_ADD(6, 1); STAT_ADD(7, dual ? 1 : 0); }
+#endif
+  }
 
-    float r0, r1, g0, g1, b0, b1;
-    upk(cr, r0, r1); upk(cg, g0, g1); upk(cb, b0, b1);
+  unit_sync(nsync);
+  uint32_t any_fail = 0;
+  for (uint32_t q = 0; q < ng; ++q) any_fail |= S.fail[q];
+  if (!any_fail) break;
+  suffix = (suffix > 0x10000000u) ? 0xFFFFFFFFu : suffix * BL_SUFFIX_GROWTH;
+  if (tid < BL_SLOTS) {
+    mbar_inval(&S.full[tid]);
+    mbar_inval(&S.empty[tid]);
+  }
+  }   // attempts
+
+  if (w >= BL_PRODUCER_THREADS / 32) {
+    // epilogue: pack RGB, resolve the alpha byte (E7), write the pixel
+    const uint32_t g = g0 + (w - BL_PRODUCER_THREADS / 32);
+    const uint32_t px = tx0 + 8u * (g & 1u) + (lane & 7u);
+    const uint32_t py0 = ty0 + 8u * (g >> 1) + (lane >> 3), py1 = py0 + 4u;
+    const bool inside0 = px < P.W && py0 < P.row1, inside1 = px < P.W && py1 < P.row1;
+    const float sx = (float)px + P.sample_off;
+    const float sy0 = (float)py0 + P.sample_off, sy1 = (float)py1 + P.sample_off;
+    uint32_t *pix0 = fb_rows + (size_t)(py0 - P.row0) * P.W + px;
+    uint32_t *pix1 = pix0 + (size_t)4u * P.W;
+    float r0, r1, g0f, g1f, b0, b1;
+    upk(cr, r0, r1); upk(cg, g0f, g1f); upk(cb, b0, b1);
     if (inside0 && last0 != 0xFFFFFFFFu) {
       // fragment() of the last covering entry for this pixel (pipelines.rs:127-145)
       const float4 *rp = reinterpret_cast<const float4 *>(recs + last0);
       const float la = fragment_alpha(sx, sy0, __ldg(rp), __ldg(rp + 1));
-      const uint32_t r = (uint32_t)__fmul_rn(r0, 255.0f), gg = (uint32_t)__fmul_rn(g0, 255.0f);
+      const uint32_t r = (uint32_t)__fmul_rn(r0, 255.0f), gg = (uint32_t)__fmul_rn(g0f, 255.0f);
       const uint32_t bl = (uint32_t)__fmul_rn(b0, 255.0f), av = (uint32_t)__fmul_rn(la, 255.0f);
       *pix0 = bl | (gg << 8) | (r << 16) | (av << 24);
     }
     if (inside1 && last1 != 0xFFFFFFFFu) {
       const float4 *rp = reinterpret_cast<const float4 *>(recs + last1);
       const float la = fragment_alpha(sx, sy1, __ldg(rp), __ldg(rp + 1));
-      const uint32_t r = (uint32_t)__fmul_rn(r1, 255.0f), gg = (uint32_t)__fmul_rn(g1, 255.0f);
+      const uint32_t r = (uint32_t)__fmul_rn(r1, 255.0f), gg = (uint32_t)__fmul_rn(g1f, 255.0f);
       const uint32_t bl = (uint32_t)__fmul_rn(b1, 255.0f), av = (uint32_t)__fmul_rn(la, 255.0f);
       *pix1 = bl | (gg << 8) | (r << 16) | (av << 24);
     }

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -452,6 +453,23 @@ int splat_get_timings(splat_ctx *c, splat_timings *t) {
   t->n_instances = c->last_instances;
   t->n_tiles = c->last_tiles;
   t->kernel_launches = c->launches;
+  return SPLAT_OK;
+}
+
+int splat_get_tile_loads(splat_ctx *c, uint32_t *per_tile, uint64_t cap, uint64_t *n_tiles) {
+  if (!c || !per_tile || !n_tiles) return SPLAT_ERR_INVALID;
+  if (!c->have_frame) return fail(c, SPLAT_ERR_STATE, "no frame rendered yet");
+  CU(cudaSetDevice(c->cfg.device));
+  CU(cudaEventSynchronize(c->ev[EV_BLEND]));
+  const uint64_t T = c->last_tiles, m = std::min<uint64_t>(cap, T);
+  *n_tiles = T;
+  if (c->last_instances == 0) { std::memset(per_tile, 0, m * sizeof(uint32_t)); return SPLAT_OK; }
+  uint2 *h = static_cast<uint2 *>(std::malloc(std::max<uint64_t>(m, 1) * sizeof(uint2)));
+  if (!h) return fail(c, SPLAT_ERR_NOMEM, "host allocation");
+  cudaError_t e = cudaMemcpy(h, c->ranges, m * sizeof(uint2), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) for (uint64_t t = 0; t < m; ++t) per_tile[t] = h[t].y - h[t].x;
+  std::free(h);
+  if (e != cudaSuccess) return fail(c, SPLAT_ERR_CUDA, "tile loads", e);
   return SPLAT_OK;
 }
 

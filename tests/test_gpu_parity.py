@@ -146,6 +146,36 @@ def test_blends_onto_existing_contents(lib, orc):
     assert np.count_nonzero(fb == fb0) > 0 and np.count_nonzero(fb != fb0) > 0
 
 
+DEEP = [
+    # name, n, seed, W, H, camera z, log_scale_mean, opacity override, random initial framebuffer
+    ("deep_150k_128x96", 150_000, 0x5EED0051, 128, 96, 3.0, -2.5, None, False),
+    ("deep_onto_noise", 120_000, 0x5EED0052, 100, 70, 3.0, -2.5, None, True),
+    ("deep_faint_opacity", 120_000, 0x5EED0053, 96, 64, 3.0, -2.5, 0.03, True),
+    ("deep_mixed_opacity", 200_000, 0x5EED0054, 160, 96, 2.5, -2.8, "mixed", True),
+]
+
+
+@pytest.mark.parametrize("case", DEEP, ids=[c[0] for c in DEEP])
+def test_deep_lists_exact_early_termination(lib, orc, case):
+    """Tile lists of thousands of entries: the blend kernel composites only a suffix of each list
+    (both extreme start states, monotone byte maps) and must still be bit-identical to walking
+    the whole list -- including pixels that never converge (faint opacities) and a non-trivial
+    buffer to blend onto."""
+    name, n, seed, W, H, camz, lsm, op, noise = case
+    scene = _scene(n, seed, lsm)
+    if op == "mixed":
+        scene.opacities[::2] = 0.01
+    elif op is not None:
+        scene.opacities[:] = op
+    cam = _camera(W, H, (0.0, 0.0, camz))
+    fb0 = None
+    if noise:
+        fb0 = np.random.default_rng(seed).integers(0, 2 ** 32, size=(H, W), dtype=np.uint64).astype(np.uint32)
+    fb, ref, t, st = _render_both(lib, orc, scene, cam, W, H, fb0=fb0)
+    assert t["n_instances"] / t["n_tiles"] > 1500, "lists too short to exercise the suffix path"
+    assert np.array_equal(fb, ref), f"{np.count_nonzero(fb != ref)} of {W*H} pixels differ"
+
+
 @pytest.mark.parametrize("y_down,zclip", [(0, 0), (1, 1), (0, 2)])
 def test_euc_switches(lib, orc, y_down, zclip):
     W, H = 400, 300

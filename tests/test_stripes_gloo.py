@@ -1,0 +1,135 @@
+"""Multi-GPU host logic without a GPU: stripe partition + grouped send/recv gather at world
+size 2 over gloo.  Each rank "renders" its stripe with the CPU oracle (the checker standing in
+for the device here) into its rows of a full frame; after the gather rank 0 must hold exactly
+the single-process full-frame render."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+from splat_b200 import stripes  # noqa: E402
+
+
+def test_equal_bounds_cover_and_align():
+    for H in (1080, 130, 16, 17, 2160):
+        for world in (1, 2, 3, 4, 8):
+            b = stripes.stripe_bounds(H, world)
+            assert len(b) == world
+            stripes.check_bounds(b, H)
+    # more ranks than tile rows: the surplus ranks get empty stripes
+    b = stripes.stripe_bounds(40, 8)
+    stripes.check_bounds(b, 40)
+    assert sum(1 for r0, r1 in b if r1 > r0) == 3
+
+
+def test_balanced_bounds_minimise_the_heaviest_stripe():
+    rng = np.random.default_rng(7)
+    for H, world in ((1080, 2), (1080, 4), (1080, 8), (720, 3), (330, 4)):
+        tr = stripes.tile_rows(H)
+        w = rng.gamma(0.5, 1.0, tr) * np.exp(-((np.arange(tr) - tr / 2.0) / (tr / 6.0)) ** 2)  # centre-heavy
+        b = stripes.stripe_bounds(H, world, w)
+        stripes.check_bounds(b, H)
+        loads = [w[r0 // 16:(r1 + 15) // 16].sum() for r0, r1 in b]
+        # brute-force optimum by dynamic programming
+        pre = np.concatenate([[0.0], np.cumsum(w)])
+        best = np.full((world + 1, tr + 1), np.inf)
+        best[0, 0] = 0.0
+        for k in range(1, world + 1):
+            for e in range(tr + 1):
+                for s in range(e + 1):
+                    best[k, e] = min(best[k, e], max(best[k - 1, s], pre[e] - pre[s]))
+        assert max(loads) <= best[world, tr] * (1 + 1e-9) + 1e-9
+        eq = stripes.stripe_bounds(H, world)
+        assert max(loads) <= max(w[r0 // 16:(r1 + 15) // 16].sum() for r0, r1 in eq) + 1e-12
+
+
+def test_bad_bounds_are_rejected():
+    with pytest.raises(ValueError):
+        stripes.check_bounds([(0, 100), (100, 330)], 330)       # not tile aligned
+    with pytest.raises(ValueError):
+        stripes.check_bounds([(0, 160), (176, 330)], 330)       # gap
+    with pytest.raises(ValueError):
+        stripes.stripe_bounds(330, 2, [1.0, 2.0])               # wrong number of rows
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, balanced, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+
+    from oracle import oracle as orc
+    from splat_b200 import stripes as st
+    from splat_b200.camera import Camera
+    from splat_b200.gaussians import synthetic_scene
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        W, H = 200, 150
+        dev = torch.device("cpu")
+        scene = synthetic_scene(1500, seed=0x5EED0041, log_scale_mean=-3.0) if rank == 0 else None
+        scene = st.broadcast_scene(scene, rank, dev)                 # C0
+        cam = Camera(H, W, (0.0, 0.0, 4.0))
+        cam.update_camera_pose()
+        ocam, cfg = orc.camera_from(cam), orc.make_config(lowpass=0.3, nthreads=2)
+        sp = orc.project(scene, ocam, cfg, W, H)
+        order = orc.sort_visible(sp)
+        bounds = None
+        if rank == 0:
+            row_load = None
+            if balanced:   # stand-in for Context.tile_loads: 3-sigma rects per tile row
+                cy, hy = sp["cyp"], sp["bbox"][:, 1]
+                vis = sp["visible"] != 0
+                row_load = np.zeros(st.tile_rows(H))
+                for t in range(len(row_load)):
+                    row_load[t] = np.count_nonzero(vis & (cy + hy >= 16 * t) & (cy - hy < 16 * (t + 1)))
+            bounds = st.stripe_bounds(H, world, row_load)
+        bounds = st.broadcast_bounds(bounds, world, dev)
+        st.check_bounds(bounds, H)
+        r0, r1 = bounds[rank]
+        fb = np.full((H, W), 0x00102030, np.uint32)                  # blended onto, not cleared
+        if rank != 0:
+            fb[:r0] = 0xDEADBEEF                                     # rows a rank does not own are garbage
+            fb[r1:] = 0xDEADBEEF
+        if r1 > r0:
+            orc.rasterize_rows(sp, order, cfg, fb, np.arange(r0, r1))
+        t = torch.from_numpy(fb.view(np.int32))
+        st.gather_stripes(t, bounds, rank)                           # C1
+        if rank == 0:
+            # rank 0's own rows outside its stripe were still the initial value before the gather
+            ref = np.full((H, W), 0x00102030, np.uint32)
+            orc.rasterize_rows(sp, order, cfg, ref, np.arange(0, H))
+            q.put((bool(np.array_equal(fb, ref)), int(np.count_nonzero(fb != ref)), bounds))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("balanced", [False, True])
+def test_world_size_2_gather_equals_full_frame(balanced):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, balanced, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok, bad, bounds = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok, f"{bad} pixels differ after the gather (bounds {bounds})"
+    assert bounds[0][1] == bounds[1][0] and bounds[1][1] == 150

@@ -31,7 +31,7 @@ def main():
     cams = bench.orbit_cameras(a.width, a.height, a.frames)
     fb = np.zeros((a.height, a.width), np.uint32)
     names = ["group_entries_evaluated", "group_entries_to_consumer", "pixel_pairs_alpha_gt0",
-             "list_entries_staged", "candidate_pairs", "lanes_alpha_gt0"]
+             "list_entries_staged", "candidate_pairs", "lanes_alpha_gt0", "suffix_attempts", "suffix_attempts_failed"]
     ctx.debug_blend_stats(reset=True)
     for i, c in enumerate(cams):
         fb[:] = 0
