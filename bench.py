@@ -123,18 +123,6 @@ class _CamView:
     def get_htanfovxy_focal(self): return self.hf
 
 
-def stripe_bounds(H, world):
-    """tile-row stripes, equal numbers of tile rows (remainder to the first ranks)"""
-    trows = (H + TILE - 1) // TILE
-    base, rem = divmod(trows, world)
-    bounds, r = [], 0
-    for k in range(world):
-        t = base + (1 if k < rem else 0)
-        bounds.append((min(r * TILE, H), min((r + t) * TILE, H)))
-        r += t
-    return bounds
-
-
 # ----------------------------------------------------------------------------- CPU arm
 def cpu_frame_time(orc, scene, cov3d, camt, W, H, row_step, nthreads):
     """One frame of the CPU restatement: project + stable sort over the whole scene, then the
@@ -198,7 +186,8 @@ def workload_config(args, world):
     return {"workload": f"C3 bicycle-sized synthetic scene: {args.n} Gaussians (seed 0x{SEED:X}), "
                         f"{args.width}x{args.height}, camera (0,0,5) orbiting 10 deg yaw/frame, Pipeline02 (low-pass 0.3)",
             "n_gaussians": args.n, "width": args.width, "height": args.height,
-            "parallelism": f"screen-tile stripes x{world}" if world > 1 else "single GPU",
+            "parallelism": (f"screen-tile stripes x{world}, " + ("equal" if args.equal_stripes else "balanced from a probe frame")
+                            + ", scene replicated, one NCCL send/recv gather per frame") if world > 1 else "single GPU",
             "l2_policy": "inputs larger than L2 (scene 160 B x N, per-frame buffers > 126 MB); no explicit flush"}
 
 
@@ -223,44 +212,40 @@ def run_ours(args):
     K, Wm = args.steps, args.warmup
 
     # ---- scene: generated on rank 0, broadcast once over NCCL (C0), uploaded on every rank
-    shapes = [(n, 4), (n, 3), (n,), (n, 4), (n, 48)]
-    if rank == 0:
-        sc = make_scene(n)
-        host = [sc.positions, sc.scales, sc.opacities, sc.rotations, sc.sh]
-    if world > 1:
-        arrs = []
-        for i, shp in enumerate(shapes):
-            t = torch.from_numpy(host[i]).to(dev) if rank == 0 else torch.empty(shp, dtype=torch.float32, device=dev)
-            dist.broadcast(t, 0)
-            arrs.append(t.cpu().numpy())
-            del t
-        from splat_b200.gaussians import GaussianList
-        sc = GaussianList(*arrs)
-        torch.cuda.empty_cache()
+    from splat_b200 import stripes
+    sc = stripes.broadcast_scene(make_scene(n) if rank == 0 else None, rank, dev)
+    torch.cuda.empty_cache()
     ctx = _lib.Context(device=local, lowpass=LOWPASS)
     t0 = time.time()
     ctx.upload(sc)
     log(f"[bench] rank {rank}: scene uploaded in {time.time() - t0:.1f}s")
 
-    bounds = stripe_bounds(H, world)
-    r0, r1 = bounds[rank]
     cams_all = orbit_cameras(W, H, 2 * (Wm + K))
     cam_structs = [_lib.camera_struct(_CamView(c)) for c in cams_all]
 
     fb_dev = torch.zeros((H, W), dtype=torch.int32, device=dev)   # full frame; this rank owns rows r0:r1
     stream = torch.cuda.current_stream()
 
+    # ---- stripes: rank 0 renders one probe frame (untimed, once per scene) and places the
+    # stripe boundaries so that the heaviest stripe is as light as possible
+    bounds = None
+    if rank == 0:
+        row_load = None
+        if world > 1 and not args.equal_stripes:
+            ctx.render_device(cam_structs[0], fb_dev.data_ptr(), W, H, 0, H, stream.cuda_stream)
+            tl = ctx.tile_loads((W + TILE - 1) // TILE).astype(np.float64)
+            # blend cost of a tile: its list up to the early-termination depth, plus a constant
+            row_load = (np.minimum(tl, 4096.0) + 64.0).sum(axis=1) + 0.35 * tl.sum(axis=1) / 16.0
+            fb_dev.zero_()
+        bounds = stripes.stripe_bounds(H, world, row_load)
+    bounds = stripes.broadcast_bounds(bounds, world, dev)
+    stripes.check_bounds(bounds, H)
+    r0, r1 = bounds[rank]
+    log(f"[bench] rank {rank}: rows [{r0},{r1})")
+
     def gather_frame():
         """C1: stripes -> rank 0's full frame, straight from/into the render target (no staging)."""
-        if world == 1:
-            return
-        if rank == 0:
-            ops = [dist.P2POp(dist.irecv, fb_dev[b0:b1], k) for k, (b0, b1) in enumerate(bounds) if k != 0 and b1 > b0]
-        else:
-            ops = [dist.P2POp(dist.isend, fb_dev[r0:r1], 0)] if r1 > r0 else []
-        if ops:
-            for w_ in dist.batch_isend_irecv(ops):
-                w_.wait()
+        stripes.gather_stripes(fb_dev, bounds, rank)
 
     def frame_device(i):
         if r1 > r0:
@@ -401,6 +386,7 @@ def main():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--cpu-row-step", type=int, default=0, help="CPU sample: every k-th tile stripe (0 = default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--equal-stripes", action="store_true", help="N > 1: equal tile-row stripes instead of load-balanced ones")
     args = ap.parse_args()
     if args.warmup < 3:
         log("[bench] warm-up raised to 3 (timing rules)")

@@ -33,43 +33,52 @@ tile_count_kernel(const uint32_t *__restrict__ sorted_keys, const uint32_t *__re
   if ((threadIdx.x & 31) == 0 && b) atomicAdd(&status->n_visible, (unsigned int)__popc(b));
 }
 
-// Warp-cooperative duplication: the warp walks its 32 Gaussians one at a time and its lanes
-// write that Gaussian's tiles, so big quads (thousands of tiles) are spread over 32 lanes and
-// the stores of one Gaussian are contiguous.  key = stripe-local tile id, value = Gaussian
-// index; emission order = depth rank, which the stable tile sort preserves.
+// Duplication, load-balanced over OUTPUT positions: a CTA owns 256 consecutive depth ranks, whose
+// instances form one contiguous output range [offs[r0], offs[r0+256)).  The CTA walks that range
+// 256 positions at a time; thread j finds its rank with an 8-step binary search over the 256
+// offsets in shared memory, so a quad that covers thousands of tiles is spread over the whole
+// CTA, consecutive threads write consecutive positions (fully coalesced 4-byte stores), and no
+// lane idles on small quads.  key = stripe-local tile id, value = Gaussian index; emission
+// order = depth rank, which the stable tile sort preserves.
 __global__ void __launch_bounds__(256)
 emit_instances_kernel(const uint32_t *__restrict__ order, const uint2 *__restrict__ rects,
                       const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ offs,
                       uint32_t *__restrict__ inst_keys, uint32_t *__restrict__ inst_vals, uint32_t n,
                       uint32_t tiles_x) {
-  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t lane = threadIdx.x & 31u;
-  uint32_t my_cnt = 0, my_off = 0, my_idx = 0;
-  uint2 my_rect = make_uint2(0, 0);
+  __shared__ uint32_t s_off[257];
+  __shared__ uint32_t s_idx[256];
+  __shared__ uint2 s_rect[256];
+  const uint32_t tid = threadIdx.x, r0 = blockIdx.x * 256u, r = r0 + tid;
+  const uint32_t last = min(n, r0 + 256u) - 1u;     // last valid rank of this CTA (r0 < n always)
+  uint32_t c = 0, o = 0;
   if (r < n) {
-    my_cnt = cnt[r];
-    if (my_cnt) {
-      my_off = offs[r];
-      my_idx = order[r];
-      my_rect = rects[my_idx];
+    c = cnt[r];
+    o = offs[r];
+    s_off[tid] = o;
+    if (c) {
+      const uint32_t gi = order[r];
+      s_idx[tid] = gi;
+      s_rect[tid] = rects[gi];
     }
+    if (r == last) s_off[256] = o + c;
   }
-  uint32_t todo = __ballot_sync(0xFFFFFFFFu, my_cnt != 0);
-  while (todo) {
-    const int src = __ffs(todo) - 1;
-    todo &= todo - 1;
-    const uint32_t c = __shfl_sync(0xFFFFFFFFu, my_cnt, src);
-    const uint32_t o = __shfl_sync(0xFFFFFFFFu, my_off, src);
-    const uint32_t g = __shfl_sync(0xFFFFFFFFu, my_idx, src);
-    const uint32_t rx = __shfl_sync(0xFFFFFFFFu, my_rect.x, src);
-    const uint32_t ry = __shfl_sync(0xFFFFFFFFu, my_rect.y, src);
-    const uint32_t x0 = rx & 0xFFFFu, y0 = rx >> 16, x1 = ry & 0xFFFFu;
-    const uint32_t wdt = x1 - x0 + 1;
-    for (uint32_t k = lane; k < c; k += 32) {
-      const uint32_t ty = y0 + k / wdt, tx = x0 + k % wdt;
-      inst_keys[o + k] = ty * tiles_x + tx;
-      inst_vals[o + k] = g;
-    }
+  __syncthreads();
+  const uint32_t begin = s_off[0], end = s_off[256];
+  if (r >= n) s_off[tid] = end;     // only in the last CTA; read by the search below
+  __syncthreads();
+  for (uint32_t j = begin + tid; j < end; j += 256u) {
+    // largest k in [0,255] with s_off[k] <= j  (zero-count ranks share their successor's offset,
+    // so this lands on the rank that really owns position j)
+    uint32_t k = 0;
+#pragma unroll
+    for (uint32_t step = 128u; step > 0u; step >>= 1)
+      if (s_off[k + step] <= j) k += step;
+    const uint32_t q = j - s_off[k];
+    const uint2 rc = s_rect[k];
+    const uint32_t x0 = rc.x & 0xFFFFu, y0 = rc.x >> 16, wdt = (rc.y & 0xFFFFu) - x0 + 1u;
+    const uint32_t row = q / wdt, col = q - row * wdt;
+    inst_keys[j] = (y0 + row) * tiles_x + x0 + col;
+    inst_vals[j] = s_idx[k];
   }
 }
 

@@ -64,7 +64,7 @@ constexpr int BL_BATCH = 256;                      // list entries staged per ro
 constexpr int BL_CH = 8;                           // list entries per ring chunk
 constexpr int BL_SLOTS = 16;                       // ring chunk slots per CTA, split among the unit's groups
 #ifndef SPLAT_SUFFIX0
-#define SPLAT_SUFFIX0 512
+#define SPLAT_SUFFIX0 256
 #endif
 #ifndef SPLAT_SUFFIX_GROWTH
 #define SPLAT_SUFFIX_GROWTH 4
@@ -264,7 +264,12 @@ unit_order_kernel(const uint2 *__restrict__ ranges, uint32_t T, uint2 *__restric
   for (int i = threadIdx.x; i < NB; i += blockDim.x) hist[i] = 0;
   __syncthreads();
   const unsigned long long I = *n_instances;
+#ifdef SPLAT_NO_SPLIT
+  const uint32_t t4 = 0xFFFFFFFFu, t2 = 0xFFFFFFFFu;
+  (void)I;
+#else
   const uint32_t t4 = (uint32_t)max(4096ull, I / 800ull), t2 = (uint32_t)max(2048ull, I / 3200ull);
+#endif
   auto bucket = [](uint32_t len) -> uint32_t {
     const int b = (int)(16.0f * __log2f((float)len));   // 0 .. 16*32-1
     return (uint32_t)max(0, NB - 1 - b);

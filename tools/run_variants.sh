@@ -7,3 +7,8 @@ done
 if [ -f splat_b200/libsplat_b200_stats.so ]; then
   SPLAT_B200_LIB=$PWD/splat_b200/libsplat_b200_stats.so timeout 300 python tools/blend_stats.py 2>/dev/null
 fi
+for v in build/var/stats_*.so; do
+  [ -f "$v" ] || continue
+  echo "== stats: $v"
+  SPLAT_B200_LIB=$PWD/$v timeout 300 python tools/blend_stats.py --frames 2 2>/dev/null
+done
