@@ -83,14 +83,29 @@ emit_instances_kernel(const uint32_t *__restrict__ order, const uint2 *__restric
 }
 
 // ranges[t] = [start, end) of tile t in the tile-sorted instance list (zeroed beforehand).
+// Four keys per thread (one 16-byte load) plus the two neighbours across the group boundary.
 __global__ void __launch_bounds__(256)
 tile_ranges_kernel(const uint32_t *__restrict__ sorted_tile_keys, uint32_t n,
                    uint2 *__restrict__ ranges) {
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
   if (j >= n) return;
-  const uint32_t t = sorted_tile_keys[j];
-  if (j == 0 || sorted_tile_keys[j - 1] != t) ranges[t].x = j;
-  if (j + 1 == n || sorted_tile_keys[j + 1] != t) ranges[t].y = j + 1;
+  uint32_t k[6];   // k[0] = key[j-1], k[1..4] = key[j..j+3], k[5] = key[j+4]
+  if (j + 4u <= n) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(sorted_tile_keys + j);
+    k[1] = v.x; k[2] = v.y; k[3] = v.z; k[4] = v.w;
+  } else {
+#pragma unroll
+    for (uint32_t q = 0; q < 4u; ++q) k[1 + q] = (j + q < n) ? sorted_tile_keys[j + q] : 0xFFFFFFFFu;
+  }
+  k[0] = j ? sorted_tile_keys[j - 1u] : 0xFFFFFFFFu;
+  k[5] = (j + 4u < n) ? sorted_tile_keys[j + 4u] : 0xFFFFFFFFu;
+#pragma unroll
+  for (uint32_t q = 0; q < 4u; ++q) {
+    if (j + q >= n) break;
+    const uint32_t t = k[1 + q];
+    if (j + q == 0u || k[q] != t) ranges[t].x = j + q;
+    if (j + q + 1u == n || k[2 + q] != t) ranges[t].y = j + q + 1u;
+  }
 }
 
 }  // namespace splat

@@ -9,8 +9,8 @@
 // and whose tile-digit passes run on the I tile instances.  Stability of every pass keeps
 // equal depths in ascending Gaussian index, exactly like the reference's stable sort.
 //
-// Per pass: histogram per 4096-key block -> exclusive scan over the (digit, block) table ->
-// scatter.  The scatter ranks keys with warp match-any (stable), reorders the block in shared
+// Per pass: histogram per 4096-key block -> per-digit exclusive scan over the blocks ->
+// scatter (3 launches).  The scatter ranks keys with warp match-any (stable), reorders the block in shared
 // memory so that each digit's run is written with coalesced stores.
 // Algorithmic bytes per pass: 4 (hist read) + 8 (read) + 8 (write) = 20 B per pair.
 #pragma once
@@ -28,7 +28,9 @@ SPLAT_DEVINL uint32_t rs_count(const uint32_t *n_ptr, uint32_t n_fixed) {
   return n_ptr ? *n_ptr : n_fixed;
 }
 
-// hist[d * nblk + blk] = number of keys of block blk whose digit is d
+// hist[d * nblk + blk] = number of keys of block blk whose digit is d.
+// All 16 keys of a thread are loaded first (four 16-byte loads in flight), then counted with
+// shared-memory atomics.
 __global__ void __launch_bounds__(RS_THREADS)
 rs_hist_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ n_ptr, uint32_t n_fixed,
                int shift, uint32_t *__restrict__ hist, uint32_t nblk) {
@@ -37,7 +39,19 @@ rs_hist_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ n
   const uint32_t base = blockIdx.x * RS_BLOCK;
   h[threadIdx.x] = 0;
   __syncthreads();
-  if (base < n) {
+  if (base + RS_BLOCK <= n) {
+    uint4 v[RS_ITEMS / 4];
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS / 4; ++k)
+      v[k] = __ldg(reinterpret_cast<const uint4 *>(keys + base) + k * RS_THREADS + threadIdx.x);
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS / 4; ++k) {
+      atomicAdd(&h[(v[k].x >> shift) & 0xFFu], 1u);
+      atomicAdd(&h[(v[k].y >> shift) & 0xFFu], 1u);
+      atomicAdd(&h[(v[k].z >> shift) & 0xFFu], 1u);
+      atomicAdd(&h[(v[k].w >> shift) & 0xFFu], 1u);
+    }
+  } else if (base < n) {
 #pragma unroll
     for (int k = 0; k < RS_ITEMS; ++k) {
       const uint32_t idx = base + k * RS_THREADS + threadIdx.x;
@@ -48,11 +62,49 @@ rs_hist_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ n
   hist[threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
 }
 
+// One CTA per digit d: exclusive scan of hist[d][0..nblk) in place (where block blk's keys with
+// digit d start inside the digit's run) and the digit total into tot[d].  The scatter kernel adds
+// the digit's global base itself (an exclusive scan of the 256 totals), so a pass is three
+// launches: histogram, this, scatter.
+constexpr int RW_THREADS = 1024;
+__global__ void __launch_bounds__(RW_THREADS)
+rs_rowscan_kernel(uint32_t *__restrict__ hist, uint32_t nblk, uint32_t *__restrict__ tot) {
+  __shared__ uint32_t wsum[RW_THREADS / 32];
+  __shared__ uint32_t carry_s;
+  uint32_t *row = hist + (size_t)blockIdx.x * nblk;
+  const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < nblk; base += RW_THREADS) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = (i < nblk) ? row[i] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= (uint32_t)o) incl += t;
+    }
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    uint32_t wb = 0;
+    for (uint32_t q = 0; q < w; ++q) wb += wsum[q];
+    const uint32_t carry = carry_s;
+    if (i < nblk) row[i] = carry + wb + incl - v;
+    __syncthreads();
+    if (threadIdx.x == RW_THREADS - 1) carry_s = carry + wb + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) tot[blockIdx.x] = carry_s;
+}
+
+// NB = 8: all eight digit bits (fully unrolled ranking); NB = 0: `nbits` < 8 bits at run time
+// (the last pass of a key whose width is not a multiple of 8).
+template <int NB>
 __global__ void __launch_bounds__(RS_THREADS)
 rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                   uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
-                  const uint32_t *__restrict__ n_ptr, uint32_t n_fixed, int shift,
-                  const uint32_t *__restrict__ hist_scanned, uint32_t nblk) {
+                  const uint32_t *__restrict__ n_ptr, uint32_t n_fixed, int shift, int nbits,
+                  const uint32_t *__restrict__ hist_scanned, const uint32_t *__restrict__ tot_g, uint32_t nblk) {
   __shared__ uint32_t cnt[RS_WARPS][256];   // per-warp digit counts, then exclusive warp bases
   __shared__ uint32_t dbase[256];           // block-local start of each digit's run
   __shared__ uint32_t gofs[256];            // global offset of the run minus dbase
@@ -71,23 +123,35 @@ rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
   for (int q = 0; q < RS_WARPS; ++q) cnt[q][tid] = 0;
   __syncthreads();
 
-  uint32_t key[RS_ITEMS], val[RS_ITEMS];
+  // Stable ranking inside the warp.  The lanes that hold the same digit ("peers") are found with
+  // one ballot per digit bit; match.any would do it in one instruction, but on sm_100 it keeps
+  // the ADU pipe busy for ~64 cycles per warp instruction (ncu r1h: pipe_adu 76%, the limiter of
+  // this kernel), a ballot for 2.  The digit's first lane bumps the warp's counter; rank = old
+  // count + number of peers in lower lanes, so equal digits keep their input order.
+  uint32_t key[RS_ITEMS];
   uint16_t rank[RS_ITEMS];
 #pragma unroll
   for (int k = 0; k < RS_ITEMS; ++k) {
     const uint32_t li = w * RS_WARP_SPAN + k * 32 + lane;   // index order == (warp, round, lane)
+    key[k] = (li < nvalid) ? keys_in[base + li] : 0xFFFFFFFFu;
+  }
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    const uint32_t li = w * RS_WARP_SPAN + k * 32 + lane;
     const bool valid = li < nvalid;
-    key[k] = valid ? keys_in[base + li] : 0xFFFFFFFFu;
-    val[k] = valid ? vals_in[base + li] : 0u;
     const uint32_t d = (key[k] >> shift) & 0xFFu;
-    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, valid ? d : 0x100u);
+    uint32_t peers = __ballot_sync(0xFFFFFFFFu, valid);
+    const int nb = NB ? NB : nbits;
+#pragma unroll
+    for (int b = 0; b < nb; ++b) {
+      const bool bit = (d >> b) & 1u;
+      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, bit);
+      peers &= bit ? bal : ~bal;
+    }
     const int leader = __ffs(peers) - 1;
     uint32_t old = 0;
-    if (valid && (int)lane == leader) {
-      old = cnt[w][d];
-      cnt[w][d] = old + __popc(peers);
-    }
-    old = __shfl_sync(0xFFFFFFFFu, old, leader);
+    if (valid && (int)lane == leader) old = atomicAdd(&cnt[w][d], (uint32_t)__popc(peers));
+    old = __shfl_sync(0xFFFFFFFFu, old, leader & 31);
     rank[k] = (uint16_t)(old + __popc(peers & lt_mask));
     __syncwarp();
   }
@@ -115,7 +179,21 @@ rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
   for (int q = 0; q < RS_WARPS; ++q) wbase += (q < (int)w) ? wsum[q] : 0u;
   const uint32_t excl = wbase + incl - tot;
   dbase[tid] = excl;
-  gofs[tid] = hist_scanned[tid * nblk + blockIdx.x] - excl;
+  // global base of digit tid = exclusive scan of the 256 digit totals (rs_rowscan_kernel)
+  const uint32_t gt = tot_g[tid];
+  uint32_t gincl = gt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, gincl, o);
+    if (lane >= (uint32_t)o) gincl += t;
+  }
+  __syncthreads();                 // wsum is re-used
+  if (lane == 31) wsum[w] = gincl;
+  __syncthreads();
+  uint32_t gbase = 0;
+#pragma unroll
+  for (int q = 0; q < RS_WARPS; ++q) gbase += (q < (int)w) ? wsum[q] : 0u;
+  gofs[tid] = (gbase + gincl - gt) + hist_scanned[(size_t)tid * nblk + blockIdx.x] - excl;
   __syncthreads();
 
 #pragma unroll
@@ -125,7 +203,7 @@ rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
       const uint32_t d = (key[k] >> shift) & 0xFFu;
       const uint32_t lp = dbase[d] + cnt[w][d] + rank[k];
       skey[lp] = key[k];
-      sval[lp] = val[k];
+      sval[lp] = vals_in[base + li];
     }
   }
   __syncthreads();

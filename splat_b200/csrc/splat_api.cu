@@ -44,6 +44,7 @@ struct splat_ctx {
   uint2 *rects = nullptr;
   uint32_t *cnt = nullptr, *offs = nullptr;
   uint32_t *hist = nullptr; size_t hist_cap = 0;
+  uint32_t *tot = nullptr;          // 256 digit totals of the current radix pass
   uint32_t *partial = nullptr; size_t partial_cap = 0;
   uint64_t inst_cap = 0;
   uint32_t *ikeys[2] = {nullptr, nullptr}, *ivals[2] = {nullptr, nullptr};
@@ -88,16 +89,6 @@ void dev_free(T *&p) {
 
 inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
 
-// in-place exclusive scan of m u32 values; optional 64-bit grand total
-int scan_u32(splat_ctx *c, cudaStream_t s, uint32_t *data, uint32_t m, unsigned long long *total_out) {
-  const uint32_t np = std::max(1u, cdiv(m, SC_BLOCK));
-  scan_reduce_kernel<<<np, SC_THREADS, 0, s>>>(data, c->partial, m);
-  scan_partials_kernel<<<1, 1024, 0, s>>>(c->partial, np, total_out);
-  scan_apply_kernel<<<np, SC_THREADS, 0, s>>>(data, data, c->partial, m);
-  c->launches += 3;
-  return SPLAT_OK;
-}
-
 // stable LSD radix sort of (key, value) pairs on bits [0, bits); returns the buffer index
 // (0/1) that holds the result
 int radix_sort(splat_ctx *c, cudaStream_t s, uint32_t *keys[2], uint32_t *vals[2], uint32_t n, int bits) {
@@ -106,11 +97,15 @@ int radix_sort(splat_ctx *c, cudaStream_t s, uint32_t *keys[2], uint32_t *vals[2
   const uint32_t nblk = cdiv(n, RS_BLOCK);
   for (int shift = 0; shift < bits; shift += 8) {
     rs_hist_kernel<<<nblk, RS_THREADS, 0, s>>>(keys[cur], nullptr, n, shift, c->hist, nblk);
-    c->launches += 1;
-    scan_u32(c, s, c->hist, 256u * nblk, nullptr);
-    rs_scatter_kernel<<<nblk, RS_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1],
-                                                  nullptr, n, shift, c->hist, nblk);
-    c->launches += 1;
+    rs_rowscan_kernel<<<256, RW_THREADS, 0, s>>>(c->hist, nblk, c->tot);
+    const int nbits = std::min(8, bits - shift);
+    if (nbits == 8)
+      rs_scatter_kernel<8><<<nblk, RS_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1],
+                                                       nullptr, n, shift, 8, c->hist, c->tot, nblk);
+    else
+      rs_scatter_kernel<0><<<nblk, RS_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1],
+                                                       nullptr, n, shift, nbits, c->hist, c->tot, nblk);
+    c->launches += 3;
     cur ^= 1;
   }
   return cur;
@@ -254,7 +249,7 @@ int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cuda
   CU(cudaEventRecord(c->ev[EV_TSORT], s));
   CU(cudaMemsetAsync(c->ranges, 0, (size_t)T * sizeof(uint2), s));
   if (I > 0) {
-    tile_ranges_kernel<<<cdiv(I, 256), 256, 0, s>>>(c->ikeys[icur], (uint32_t)I, c->ranges);
+    tile_ranges_kernel<<<cdiv(I, 1024), 256, 0, s>>>(c->ikeys[icur], (uint32_t)I, c->ranges);
     unit_order_kernel<<<1, 1024, 0, s>>>(c->ranges, T, c->units, c->n_units, &c->d_status->n_instances);   // heaviest first
     c->launches += 2;
   }
@@ -315,6 +310,7 @@ int splat_create(splat_ctx **out, const splat_config *cfg) {
     return bail(SPLAT_ERR_CUDA);
   if (dev_alloc(&c->d_status, 1) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
   if (dev_alloc(&c->n_units, 1) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
+  if (dev_alloc(&c->tot, 256) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
   if (cudaMallocHost(reinterpret_cast<void **>(&c->h_status), sizeof(FrameStatus)) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
   *out = c;
   return SPLAT_OK;
@@ -325,7 +321,7 @@ void splat_destroy(splat_ctx *c) {
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_scene(c);
-  dev_free(c->hist); dev_free(c->partial); dev_free(c->ranges); dev_free(c->units); dev_free(c->n_units); dev_free(c->d_status); dev_free(c->d_fb);
+  dev_free(c->hist); dev_free(c->tot); dev_free(c->partial); dev_free(c->ranges); dev_free(c->units); dev_free(c->n_units); dev_free(c->d_status); dev_free(c->d_fb);
   for (int k = 0; k < 2; ++k) { dev_free(c->ikeys[k]); dev_free(c->ivals[k]); }
   if (c->h_status) cudaFreeHost(c->h_status);
   for (int i = 0; i < EV_COUNT_; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);

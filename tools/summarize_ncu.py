@@ -3,6 +3,7 @@
 
   tools/summarize_ncu.py launches gpurun_out/launches_rN.csv  profiles/rN_launches_summary.txt
   tools/summarize_ncu.py full     gpurun_out/blend_rN.ncu-rep profiles/rN_blend_ncu.txt
+  tools/summarize_ncu.py frame    gpurun_out/frame_rN.ncu-rep profiles/rN_frame_kernels.txt   (one row per launch)
 """
 import collections
 import csv
@@ -48,6 +49,48 @@ def launches(src, dst):
     print(open(dst).read())
 
 
+def frame(src, dst, peak_gbs=None):
+    """One row per captured launch: duration, DRAM bytes, achieved DRAM GB/s against the measured
+    copy peak, and the busiest SM-side figures."""
+    import json, os
+    if peak_gbs is None:
+        try:
+            peak_gbs = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                         "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except Exception:
+            peak_gbs = 6650.0
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    def get(rec, name, scale=True):
+        if name not in hdr:
+            return float("nan")
+        i = hdr.index(name)
+        try:
+            v = float(rec[i].replace(",", ""))
+        except ValueError:
+            return float("nan")
+        u = units[i]
+        if scale:
+            v *= {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "ns": 1e-3, "us": 1.0, "ms": 1e3}.get(u, 1.0)
+        return v
+    cols = [("sm%", "sm__throughput.avg.pct_of_peak_sustained_elapsed"), ("issue%", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            ("adu%", "sm__inst_executed_pipe_adu.avg.pct_of_peak_sustained_elapsed"), ("lsu%", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_elapsed"),
+            ("fma%", "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"), ("L2hit%", "lts__t_sector_hit_rate.pct"),
+            ("warps%", "sm__warps_active.avg.pct_of_peak_sustained_active"), ("regs", "launch__registers_per_thread")]
+    with open(dst, "w") as f:
+        f.write(f"# source: {src} (ncu --set full --clock-control none; per-launch, cold-cache, serialised)\n")
+        f.write(f"# DRAM GB/s = (dram__bytes_read.sum + dram__bytes_write.sum) / gpu__time_duration; peak = {peak_gbs:.1f} GB/s measured copy\n")
+        f.write(f"{'kernel':28s} {'grid':>7s} {'us':>8s} {'rd_MB':>8s} {'wr_MB':>8s} {'GB/s':>7s} {'%peak':>6s} " + " ".join(f"{c[0]:>6s}" for c in cols) + "\n")
+        for rec in rows[2:]:
+            name = rec[hdr.index("Kernel Name")].split("(")[0].replace("splat::", "")
+            us, rd, wr = get(rec, "gpu__time_duration.sum"), get(rec, "dram__bytes_read.sum"), get(rec, "dram__bytes_write.sum")
+            gbs = (rd + wr) / (us * 1e-6) / 1e9
+            f.write(f"{name[:28]:28s} {int(get(rec, 'launch__grid_size', False)):7d} {us:8.1f} {rd / 1e6:8.1f} {wr / 1e6:8.1f} {gbs:7.0f} {100 * gbs / peak_gbs:6.1f} "
+                    + " ".join(f"{get(rec, c[1], False):6.1f}" for c in cols) + "\n")
+    print(open(dst).read())
+
+
 def full(src, dst):
     out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
@@ -63,5 +106,8 @@ def full(src, dst):
     print(open(dst).read()[:6000])
 
 
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "frame":
+    frame(sys.argv[2], sys.argv[3])
+    sys.exit(0)
 if __name__ == "__main__":
     {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
