@@ -178,7 +178,7 @@ SPLAT_DEVINL f32x2 blend_channel2(f32x2 c_old, f32x2 om, f32x2 al, float col, f3
 
 // ---------------------------------------------------------------- mbarrier / named barrier
 #ifndef SPLAT_SLEEP_NS
-#define SPLAT_SLEEP_NS 64
+#define SPLAT_SLEEP_NS 256
 #endif
 #ifndef SPLAT_SLEEP_NS_CONSUMER
 #define SPLAT_SLEEP_NS_CONSUMER 32
@@ -236,7 +236,7 @@ SPLAT_DEVINL void mbar_wait(uint64_t *bar, uint32_t parity) {
   }
 }
 #ifndef SPLAT_WAIT_CONSUMER
-#define SPLAT_WAIT_CONSUMER 0
+#define SPLAT_WAIT_CONSUMER 3
 #endif
 #ifndef SPLAT_WAIT_PRODUCER
 #define SPLAT_WAIT_PRODUCER 2

@@ -109,11 +109,11 @@ struct TileRect {
 static_assert(sizeof(TileRect) == 8, "TileRect is packed as uint2");
 
 // One thread per Gaussian: 10 coalesced float4 loads (160 B), 48 B record + 4 B key + 8 B
-// rect out.  Algorithmic bytes: 220 B per Gaussian.
+// rect + 4 B tile count out.  Algorithmic bytes: 224 B per Gaussian.
 __global__ void __launch_bounds__(256)
 project_kernel(const float4 *__restrict__ scene, const __grid_constant__ FrameParams P,
                Rec *__restrict__ recs, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
-               uint2 *__restrict__ rects) {
+               uint2 *__restrict__ rects, uint32_t *__restrict__ tcnt) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t n = P.n;
   if (i >= n) return;
@@ -243,6 +243,7 @@ project_kernel(const float4 *__restrict__ scene, const __grid_constant__ FramePa
   keys[i] = vis ? depth_key(zv) : KEY_CULLED;
   vals[i] = i;
   rects[i] = make_uint2((uint32_t)tr.x0 | ((uint32_t)tr.y0 << 16), (uint32_t)tr.x1 | ((uint32_t)tr.y1 << 16));
+  tcnt[i] = tr.count();   // 4-byte gather target for tile_count_kernel (8 per sector, stays in L2)
 }
 
 }  // namespace splat

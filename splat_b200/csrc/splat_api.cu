@@ -42,6 +42,7 @@ struct splat_ctx {
   Rec *recs = nullptr;
   uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
   uint2 *rects = nullptr;
+  uint32_t *tcnt = nullptr;        // tiles per Gaussian (by Gaussian index)
   uint32_t *cnt = nullptr, *offs = nullptr;
   uint32_t *hist = nullptr; size_t hist_cap = 0;
   uint32_t *tot = nullptr;          // 256 digit totals of the current radix pass
@@ -142,7 +143,7 @@ int ensure_instances(splat_ctx *c, uint64_t want) {
 }
 
 void free_scene(splat_ctx *c) {
-  dev_free(c->scene); dev_free(c->recs); dev_free(c->rects); dev_free(c->cnt); dev_free(c->offs);
+  dev_free(c->scene); dev_free(c->recs); dev_free(c->rects); dev_free(c->tcnt); dev_free(c->cnt); dev_free(c->offs);
   for (int k = 0; k < 2; ++k) { dev_free(c->keys[k]); dev_free(c->vals[k]); }
   c->n = 0;
   c->have_frame = false;
@@ -154,6 +155,7 @@ int alloc_scene(splat_ctx *c, uint64_t n) {
   CU(dev_alloc(&c->scene, (size_t)SCENE_PLANES * n));
   CU(dev_alloc(&c->recs, n));
   CU(dev_alloc(&c->rects, n));
+  CU(dev_alloc(&c->tcnt, n));
   CU(dev_alloc(&c->cnt, n));
   CU(dev_alloc(&c->offs, n));
   for (int k = 0; k < 2; ++k) { CU(dev_alloc(&c->keys[k], n)); CU(dev_alloc(&c->vals[k], n)); }
@@ -185,6 +187,8 @@ int make_params(splat_ctx *c, const splat_camera *cam, uint32_t W, uint32_t H, u
   P->tiles_y = cdiv(row1, TILE) - P->tile_y0;
   P->n = c->n;
   P->nz2 = 0x8000000080000000ull;
+  if ((uint64_t)P->tiles_x * P->tiles_y >= (1ull << 24))
+    return fail(c, SPLAT_ERR_UNSUPPORTED, "more than 2^24 tiles in one stripe");
   return SPLAT_OK;
 }
 
@@ -201,13 +205,13 @@ int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cuda
   c->launches = 0;
   CU(cudaEventRecord(c->ev[EV_START], s));
   CU(cudaMemsetAsync(c->d_status, 0, sizeof(FrameStatus), s));
-  project_kernel<<<cdiv(n, 256), 256, 0, s>>>(c->scene, P, c->recs, c->keys[0], c->vals[0], c->rects);
+  project_kernel<<<cdiv(n, 256), 256, 0, s>>>(c->scene, P, c->recs, c->keys[0], c->vals[0], c->rects, c->tcnt);
   c->launches += 1;
   CU(cudaEventRecord(c->ev[EV_PROJECT], s));
   const int cur = radix_sort(c, s, c->keys, c->vals, n, 32);
   c->order_buf = cur;
   CU(cudaEventRecord(c->ev[EV_DSORT], s));
-  tile_count_kernel<<<cdiv(n, 256), 256, 0, s>>>(c->keys[cur], c->vals[cur], c->rects, c->cnt, n, c->d_status);
+  tile_count_kernel<<<cdiv(n, 256), 256, 0, s>>>(c->keys[cur], c->vals[cur], c->tcnt, c->cnt, n, c->d_status);
   c->launches += 1;
   // exclusive scan cnt -> offs, grand total -> status.n_instances
   {
@@ -478,7 +482,7 @@ int splat_debug_project(splat_ctx *c, const splat_camera *cam, uint32_t W, uint3
   if (rc) return rc;
   CU(cudaSetDevice(c->cfg.device));
   CU(cudaMemsetAsync(c->recs, 0, (size_t)c->n * sizeof(Rec), c->stream));
-  project_kernel<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->scene, P, c->recs, c->keys[0], c->vals[0], c->rects);
+  project_kernel<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->scene, P, c->recs, c->keys[0], c->vals[0], c->rects, c->tcnt);
   CU(cudaGetLastError());
   if (records12) CU(cudaMemcpyAsync(records12, c->recs, (size_t)c->n * sizeof(Rec), cudaMemcpyDeviceToHost, c->stream));
   if (depth_keys) CU(cudaMemcpyAsync(depth_keys, c->keys[0], (size_t)c->n * 4, cudaMemcpyDeviceToHost, c->stream));
