@@ -39,6 +39,27 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly ONE JSON line: libraries that print banners on fd 1 (NCCL's version
+# line, for one) are sent to stderr, and the result goes out through the saved descriptor
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -178,7 +199,7 @@ def run_reference(args):
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -205,6 +226,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL prints its version banner on stdout; stdout carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()   # raises if libsplat_b200.so is missing: no CPU fallback
 
@@ -223,8 +246,13 @@ def run_ours(args):
     cams_all = orbit_cameras(W, H, 2 * (Wm + K))
     cam_structs = [_lib.camera_struct(_CamView(c)) for c in cams_all]
 
+    # One explicit (non-default) stream carries everything: clears, kernels, NCCL, copies, timing
+    # events.  torch's default stream has handle 0, which splat_render_device reads as "use the
+    # context's own stream" -- work there would not be ordered with torch's.
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     fb_dev = torch.zeros((H, W), dtype=torch.int32, device=dev)   # full frame; this rank owns rows r0:r1
-    stream = torch.cuda.current_stream()
 
     # ---- stripes: rank 0 renders one probe frame (untimed, once per scene) and places the
     # stripe boundaries so that the heaviest stripe is as light as possible
@@ -321,6 +349,10 @@ def run_ours(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_fps = K / float(e2e_s.item())
     checksum = int(host_np.astype(np.uint64).sum()) if rank == 0 else 0
+    if world > 1:
+        dsum = int((fb_dev.to(torch.int64) & 0xFFFFFFFF).sum().item())
+        log(f"[bench] rank {rank}: device frame checksum {dsum}, own rows "
+            f"{int((fb_dev[r0:r1].to(torch.int64) & 0xFFFFFFFF).sum().item())}, host copy {checksum}")
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -385,7 +417,7 @@ def run_ours(args):
                            f"tile stripe ({c['rows_sampled']} of {H} rows, {c['raster_sample_s']:.2f}s, scaled x{c['scale']:.2f}); "
                            "C restatement of the reference (oracle/), not the Rust/euc binary"),
                 "pairs_per_frame_est": c["pairs_in_rect_est"]}
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.barrier()
@@ -399,13 +431,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=6_100_000)
+    ap.add_argument("--gaussians", dest="n", type=int, default=6_100_000)
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--cpu-row-step", type=int, default=0, help="CPU sample: every k-th tile stripe (0 = default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--equal-stripes", action="store_true", help="N > 1: equal tile-row stripes instead of load-balanced ones")
     args = ap.parse_args()
+    capture_stdout()
     if args.warmup < 3:
         log("[bench] warm-up raised to 3 (timing rules)")
         args.warmup = 3

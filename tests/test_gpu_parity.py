@@ -199,6 +199,42 @@ def test_stripes_equal_full_frame(lib, orc):
         assert np.array_equal(parts, full)
 
 
+def test_render_device_stripes_into_one_device_frame(lib, orc):
+    """splat_render_device (the multi-GPU entry point): every stripe is rendered straight into its
+    rows of ONE full-frame device buffer, on a caller-owned stream, asynchronously.  The assembled
+    frame must equal the host-buffer render and the oracle."""
+    import torch
+
+    W, H = 500, 330
+    scene = _scene(20_000, 0x5EED0033, -3.5)
+    cam = _camera(W, H, (0.0, 0.0, 4.0), yaw=0.3)
+    full, ref, _, _ = _render_both(lib, orc, scene, cam, W, H)
+    assert np.array_equal(full, ref)
+    ctx = lib.Context(device=0)
+    ctx.upload(scene)
+    cs = lib.camera_struct(cam)
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        fb = torch.zeros((H, W), dtype=torch.int32, device=dev)
+        for r0, r1 in [(0, 112), (112, 240), (240, 330)]:
+            ctx.render_device(cs, fb[r0:r1].data_ptr(), W, H, r0, r1, stream.cuda_stream)
+        t = ctx.timings()          # blocks until the last stripe finished
+        got = fb.cpu().numpy().view(np.uint32)
+    assert t["n_instances"] > 0
+    assert np.array_equal(got, full), f"{np.count_nonzero(got != full)} pixels differ"
+    # the context's own stream (stream = NULL) and a non-zero frame to blend onto
+    fb0 = np.random.default_rng(5).integers(0, 2 ** 32, size=(H, W), dtype=np.uint64).astype(np.uint32)
+    want, ref0, _, _ = _render_both(lib, orc, scene, cam, W, H, fb0=fb0)
+    assert np.array_equal(want, ref0)
+    fb = torch.from_numpy(fb0.view(np.int32)).to(dev)
+    torch.cuda.synchronize()
+    ctx.render_device(cs, fb.data_ptr(), W, H, 0, H, 0)
+    ctx.timings()
+    assert np.array_equal(fb.cpu().numpy().view(np.uint32), want)
+    ctx.close()
+
+
 def test_degenerate_inputs_are_skipped(lib, orc):
     """NaN / inf / zero-quaternion / behind-camera Gaussians: culled identically, never a crash."""
     W, H = 256, 256
