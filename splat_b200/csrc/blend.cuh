@@ -200,7 +200,7 @@ SPLAT_DEVINL void mbar_arrive(uint64_t *bar) {
 // traffic and re-polls ~10^9 times per frame, 21% of all issued instructions in r1d).
 // MODE 2: test_wait, then nanosleep with a short back-off -- a sleeping warp issues nothing.
 template <int MODE>
-SPLAT_DEVINL void mbar_wait(uint64_t *bar, uint32_t parity) {
+SPLAT_DEVINL void mbar_wait(uint64_t *bar, uint32_t parity, const uint32_t *gword = nullptr) {
   if (MODE == 0) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -220,6 +220,24 @@ SPLAT_DEVINL void mbar_wait(uint64_t *bar, uint32_t parity) {
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
         "r"(parity), "r"(0x989680u)
+        : "memory");
+  } else if (MODE == 4) {
+    // Poll, and between polls park the warp on the scoreboard: a volatile global load (an L2 hit,
+    // several hundred cycles) whose result is folded into the next poll's address.  One issue
+    // slot per poll instead of one every few cycles -- nanosleep returns almost immediately
+    // here (r1h/r1l: the same ~5e7 polls per frame at 64 ns and at 256 ns).
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 t, a;\n\t"
+        "mov.b32 a, %0;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.test_wait.parity.acquire.cta.shared::cta.b64 p, [a], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "ld.volatile.global.u32 t, [%2];\n\t"
+        "and.b32 t, t, 0;\n\t"
+        "add.u32 a, %0, t;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity), "l"(gword)
         : "memory");
   } else {
     asm volatile(
@@ -498,7 +516,7 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
         const uint32_t chunk_end = min(s_end, (chunk + 1) * BL_CH);
         const uint32_t slot = (gl << d_log) + (chunk & d_mask);
         if (s % BL_CH == 0) {
-          mbar_wait<SPLAT_WAIT_PRODUCER>(&S.empty[slot], ((chunk >> d_log) & 1u) ^ 1u);
+          mbar_wait<SPLAT_WAIT_PRODUCER>(&S.empty[slot], ((chunk >> d_log) & 1u) ^ 1u, n_units);
           nout = 0;
         }
         RingEntry *slotp = &S.ring[slot][nout];
@@ -571,7 +589,7 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
       if (evaluates && (chunk & ev_mask) == p) {
         const uint32_t slot = (gl << d_log) + (chunk & d_mask);
         if (rem == 0) {
-          mbar_wait<SPLAT_WAIT_PRODUCER>(&S.empty[slot], ((chunk >> d_log) & 1u) ^ 1u);
+          mbar_wait<SPLAT_WAIT_PRODUCER>(&S.empty[slot], ((chunk >> d_log) & 1u) ^ 1u, n_units);
           nout = 0;
         }
         __syncwarp();
@@ -642,7 +660,7 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
 
     for (uint32_t chunk = 0;; ++chunk) {
       const uint32_t slot = (gl << d_log) + (chunk & d_mask);
-      mbar_wait<SPLAT_WAIT_CONSUMER>(&S.full[slot], (chunk >> d_log) & 1u);
+      mbar_wait<SPLAT_WAIT_CONSUMER>(&S.full[slot], (chunk >> d_log) & 1u, n_units);
       const uint32_t h = S.hdr[slot];
       const uint32_t n = h & 0xFFu;
       const RingEntry *ep = &S.ring[slot][0];

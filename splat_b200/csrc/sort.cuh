@@ -23,6 +23,10 @@ constexpr int RS_ITEMS = 16;
 constexpr int RS_BLOCK = RS_THREADS * RS_ITEMS;   // 4096 pairs per CTA
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_WARP_SPAN = RS_ITEMS * 32;       // 512 consecutive pairs per warp
+#ifndef SPLAT_RS_MIN_BLOCKS
+#define SPLAT_RS_MIN_BLOCKS 4
+#endif
+constexpr int RS_MIN_BLOCKS = SPLAT_RS_MIN_BLOCKS; // resident scatter CTAs per SM the register budget must allow
 
 SPLAT_DEVINL uint32_t rs_count(const uint32_t *n_ptr, uint32_t n_fixed) {
   return n_ptr ? *n_ptr : n_fixed;
@@ -100,7 +104,7 @@ rs_rowscan_kernel(uint32_t *__restrict__ hist, uint32_t nblk, uint32_t *__restri
 // NB = 8: all eight digit bits (fully unrolled ranking); NB = 0: `nbits` < 8 bits at run time
 // (the last pass of a key whose width is not a multiple of 8).
 template <int NB>
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, RS_MIN_BLOCKS)
 rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                   uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
                   const uint32_t *__restrict__ n_ptr, uint32_t n_fixed, int shift, int nbits,
