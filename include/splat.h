@@ -84,7 +84,8 @@ typedef struct {
   float    d2h_ms;       /* framebuffer download                               */
   uint32_t frames_retried; /* renders repeated because the instance buffers had to grow */
   uint64_t n_gaussians;
-  uint64_t n_visible;    /* Gaussians that pass the z clip and the degeneracy guard */
+  uint64_t n_visible;    /* Gaussians that pass the z clip and the degeneracy guard (stripe renders:
+                          * and whose quad can touch the stripe -- the others are dropped before the sort) */
   uint64_t n_instances;  /* (tile, Gaussian) pairs                                  */
   uint64_t n_tiles;      /* tiles in the rendered stripe                            */
   uint64_t kernel_launches; /* kernels launched by the last render                  */
@@ -146,7 +147,8 @@ int splat_unpin_host(void *p);
  * splat_debug_project runs K1 alone for the full frame and copies out, per Gaussian:
  *   records12: 12 floats (cxp cyp A B | C opacity hx hy | r g b power_threshold), zeros if culled;
  *   depth_keys: u32 sort key (0xFFFFFFFF = culled); tile_rects4: 4 x u16 (x0 y0 x1 y1, inclusive).
- * splat_debug_read_order returns the depth order (Gaussian indices far -> near) of the last render.
+ * splat_debug_read_order returns the depth order (Gaussian indices far -> near) of the last render
+ *   (n_visible entries; for a stripe render only the Gaussians that can touch the stripe).
  * splat_debug_sort_pairs sorts host (key,value) arrays in place on bits [0,bits) with the device
  * radix sort. */
 int splat_debug_project(splat_ctx *ctx, const splat_camera *cam, uint32_t W, uint32_t H,

@@ -22,11 +22,13 @@ SPLAT_DEVINL TileRect unpack_rect(uint2 r) {
 __global__ void __launch_bounds__(256)
 tile_count_kernel(const uint32_t *__restrict__ sorted_keys, const uint32_t *__restrict__ order,
                   const uint32_t *__restrict__ tcnt, uint32_t *__restrict__ cnt, uint32_t n,
-                  FrameStatus *__restrict__ status) {
+                  const uint32_t *__restrict__ n_sorted, FrameStatus *__restrict__ status) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  // stripe renders sort only *n_sorted pairs; the tail of the buffers is stale
+  const uint32_t ns = n_sorted ? *n_sorted : n;
   bool vis = false;
   if (r < n) {
-    vis = sorted_keys[r] != KEY_CULLED;
+    vis = r < ns && sorted_keys[r] != KEY_CULLED;
     cnt[r] = vis ? __ldg(&tcnt[order[r]]) : 0u;
   }
   // one atomic per CTA: 190k same-address atomics (one per warp) serialised in L2 and were the

@@ -25,6 +25,7 @@ struct FrameParams {
   float sample_off;
   float ysign;         // +1: y_down, -1: y-up
   int zclip_mode;
+  int stripe_cull;     // 1: drop Gaussians that cannot touch the stripe before the colour phase and the depth sort
   uint32_t W, H;       // full image size in pixels
   uint32_t row0, row1; // rendered stripe [row0,row1)
   uint32_t tiles_x;    // ceil(W/16)
@@ -48,6 +49,7 @@ struct FrameStatus {
   unsigned long long n_instances;  // total (tile, Gaussian) pairs wanted
   unsigned int n_visible;
   unsigned int pad;
+  unsigned long long n_sort;       // stripe renders: (key, index) pairs that enter the depth sort
 };
 
 #define SPLAT_DEVINL __device__ __forceinline__

@@ -108,23 +108,38 @@ struct TileRect {
 };
 static_assert(sizeof(TileRect) == 8, "TileRect is packed as uint2");
 
-// One thread per Gaussian: 10 coalesced float4 loads (160 B), 48 B record + 4 B key + 8 B
-// rect + 4 B tile count out.  Algorithmic bytes: 224 B per Gaussian.
+// One thread per Gaussian.  Geometry phase: 4 coalesced float4 loads (position/opacity, cov3d),
+// view transform, cov2d, conic, 3-sigma extents, z clip, tile rectangle.  Colour phase: 6 more
+// float4 loads (SH degrees 0..2) and the SH evaluation.  Out: 48 B record + 4 B key + 4 B index
+// + 8 B rect + 4 B tile count.  Algorithmic bytes: 160 in + 68 out = 228 B per Gaussian.
+//
+// Stripe renders (multi-GPU, P.stripe_cull): a Gaussian whose quad cannot touch this rank's
+// stripe is dropped after the geometry phase -- no SH loads, key = KEY_CULLED -- and
+// block_kept[] counts the survivors per CTA so that compact_pairs_kernel can squeeze the
+// (key, index) pairs before the depth sort: each rank then sorts only what its stripe sees.
 __global__ void __launch_bounds__(256)
 project_kernel(const float4 *__restrict__ scene, const __grid_constant__ FrameParams P,
                Rec *__restrict__ recs, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
-               uint2 *__restrict__ rects, uint32_t *__restrict__ tcnt) {
+               uint2 *__restrict__ rects, uint32_t *__restrict__ tcnt, uint32_t *__restrict__ block_kept) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t n = P.n;
-  if (i >= n) return;
-  const float4 p0 = __ldg(&scene[i]);
+  const bool valid = i < n;
+  const uint32_t ii = valid ? i : n - 1u;     // out-of-range threads recompute the last Gaussian, store nothing
+  const float4 p0 = __ldg(&scene[ii]);
   float f[36];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    const float4 v = __ldg(&scene[(size_t)(k + 1) * n + i]);
+  for (int k = 0; k < 3; ++k) {
+    const float4 v = __ldg(&scene[(size_t)(k + 1) * n + ii]);
     f[4 * k] = v.x; f[4 * k + 1] = v.y; f[4 * k + 2] = v.z; f[4 * k + 3] = v.w;
   }
-  const float *C3 = f;        // cov3d row-major
+  if (!P.stripe_cull) {   // full-frame renders need the colour of (almost) everything: all loads in flight at once
+#pragma unroll
+    for (int k = 3; k < 9; ++k) {
+      const float4 v = __ldg(&scene[(size_t)(k + 1) * n + ii]);
+      f[4 * k] = v.x; f[4 * k + 1] = v.y; f[4 * k + 2] = v.z; f[4 * k + 3] = v.w;
+    }
+  }
+  const float *C3 = f;        // cov3d row-major (f[0..8]); f[9..11] = sh[0..2]
   const float *sh = f + 9;    // sh[0..26]
   const float *V = P.view;
 
@@ -173,41 +188,23 @@ project_kernel(const float4 *__restrict__ scene, const __grid_constant__ FramePa
   const float ndx = __fdiv_rn(ps[0], ps[3]), ndy = __fdiv_rn(ps[1], ps[3]), ndz = __fdiv_rn(ps[2], ps[3]);
   const float cxp = (ndx * 0.5f + 0.5f) * (float)P.W;
   const float cyp = ((P.ysign * ndy) * 0.5f + 0.5f) * (float)P.H;
-
-  // pipelines.rs:99-100 + gaussians.rs:41-99  SH colour along normalize(position - camera.position)
-  const float d0 = p0.x - P.cam_pos[0], d1 = p0.y - P.cam_pos[1], d2 = p0.z - P.cam_pos[2];
-  const float dn = __fsqrt_rn(d0 * d0 + d1 * d1 + d2 * d2);
-  const float x = __fdiv_rn(d0, dn), y = __fdiv_rn(d1, dn), z = __fdiv_rn(d2, dn);
-  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-  const float k1y = 0.4886025119029199f * y, k1z = 0.4886025119029199f * z, k1x = 0.4886025119029199f * x;
-  const float k4 = 1.0925484305920792f * xy, k5 = -1.0925484305920792f * yz;
-  const float k6 = 0.31539156525252005f * (2.0f * zz - xx - yy);
-  const float k7 = -1.0925484305920792f * xz, k8 = 0.5462742152960396f * (xx - yy);
-  float col[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    float v = 0.28209479177387814f * sh[c];
-    v = v - k1y * sh[3 + c] + k1z * sh[6 + c] - k1x * sh[9 + c];
-    v = v + k4 * sh[12 + c] + k5 * sh[15 + c] + k6 * sh[18 + c] + k7 * sh[21 + c] + k8 * sh[24 + c];
-    col[c] = v + 0.5f;
-  }
   const float op = p0.w;
 
   // visibility: euc's z clip on the centre (all four corners share z) + degeneracy guard
+  // (everything except the colour, which the second phase adds)
   bool zok;
   if (P.zclip_mode == 0) zok = (ndz >= 0.0f && ndz < 1.0f);
   else if (P.zclip_mode == 1) zok = (ndz >= -1.0f && ndz < 1.0f);
   else zok = true;
-  const bool vis = zok && (det != 0.0f) && finitef(zv) && finitef(cA) && finitef(cB) && finitef(cC) &&
-                   finitef(hx) && finitef(hy) && finitef(col[0]) && finitef(col[1]) && finitef(col[2]) &&
-                   finitef(op) && finitef(cxp) && finitef(cyp) &&
-                   // degeneracy guard (keeps `power` finite for every on-screen pixel)
-                   fabsf(cA) <= 1e18f && fabsf(cB) <= 1e18f && fabsf(cC) <= 1e18f &&
-                   fabsf(cxp) <= 1e9f && fabsf(cyp) <= 1e9f;
+  const bool visg = zok && (det != 0.0f) && finitef(zv) && finitef(cA) && finitef(cB) && finitef(cC) &&
+                    finitef(hx) && finitef(hy) && finitef(op) && finitef(cxp) && finitef(cyp) &&
+                    // degeneracy guard (keeps `power` finite for every on-screen pixel)
+                    fabsf(cA) <= 1e18f && fabsf(cB) <= 1e18f && fabsf(cC) <= 1e18f &&
+                    fabsf(cxp) <= 1e9f && fabsf(cyp) <= 1e9f;
 
   TileRect tr;
   tr.x0 = 1; tr.x1 = 0; tr.y0 = 1; tr.y1 = 0;   // empty
-  if (vis) {
+  if (visg) {
     const double off = (double)P.sample_off;
     const double slx = 1.0 + 1e-6 * (fabs((double)cxp) + (double)hx);
     const double sly = 1.0 + 1e-6 * (fabs((double)cyp) + (double)hy);
@@ -223,6 +220,40 @@ project_kernel(const float4 *__restrict__ scene, const __grid_constant__ FramePa
     }
   }
 
+  // ---- colour phase (skipped in stripe renders for Gaussians that cannot touch the stripe)
+  bool vis = visg;
+  const bool need_colour = visg && !(P.stripe_cull && tr.count() == 0u);
+  float col[3] = {0.f, 0.f, 0.f};
+  if (need_colour) {
+    if (P.stripe_cull) {
+#pragma unroll
+      for (int k = 3; k < 9; ++k) {
+        const float4 v = __ldg(&scene[(size_t)(k + 1) * n + ii]);
+        f[4 * k] = v.x; f[4 * k + 1] = v.y; f[4 * k + 2] = v.z; f[4 * k + 3] = v.w;
+      }
+    }
+    // pipelines.rs:99-100 + gaussians.rs:41-99  SH colour along normalize(position - camera.position)
+    const float d0 = p0.x - P.cam_pos[0], d1 = p0.y - P.cam_pos[1], d2 = p0.z - P.cam_pos[2];
+    const float dn = __fsqrt_rn(d0 * d0 + d1 * d1 + d2 * d2);
+    const float x = __fdiv_rn(d0, dn), y = __fdiv_rn(d1, dn), z = __fdiv_rn(d2, dn);
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    const float k1y = 0.4886025119029199f * y, k1z = 0.4886025119029199f * z, k1x = 0.4886025119029199f * x;
+    const float k4 = 1.0925484305920792f * xy, k5 = -1.0925484305920792f * yz;
+    const float k6 = 0.31539156525252005f * (2.0f * zz - xx - yy);
+    const float k7 = -1.0925484305920792f * xz, k8 = 0.5462742152960396f * (xx - yy);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = 0.28209479177387814f * sh[c];
+      v = v - k1y * sh[3 + c] + k1z * sh[6 + c] - k1x * sh[9 + c];
+      v = v + k4 * sh[12 + c] + k5 * sh[15 + c] + k6 * sh[18 + c] + k7 * sh[21 + c] + k8 * sh[24 + c];
+      col[c] = v + 0.5f;
+    }
+    vis = finitef(col[0]) && finitef(col[1]) && finitef(col[2]);
+  } else if (P.stripe_cull) {
+    vis = false;
+  }
+  if (!vis) { tr.x0 = 1; tr.x1 = 0; tr.y0 = 1; tr.y1 = 0; }
+
   // power threshold: alpha = min(0.99, op*exp(power)) < 1/255 is certain below pth
   // (0.002 of slack in the exponent against the 1-ulp error of the pinned exp); exp is
   // flushed to zero below -87, so pth never needs to go lower.
@@ -233,17 +264,48 @@ project_kernel(const float4 *__restrict__ scene, const __grid_constant__ FramePa
     pth = (t < -87.0) ? -87.0f : (float)t;
   }
 
-  if (vis) {
-    Rec r;
-    r.a = make_float4(cxp, cyp, cA, P.ysign * cB);
-    r.b = make_float4(cC, op, hx, hy);
-    r.c = make_float4(col[0], col[1], col[2], pth);
-    recs[i] = r;
+  if (valid) {
+    if (vis) {
+      Rec r;
+      r.a = make_float4(cxp, cyp, cA, P.ysign * cB);
+      r.b = make_float4(cC, op, hx, hy);
+      r.c = make_float4(col[0], col[1], col[2], pth);
+      recs[i] = r;
+    }
+    keys[i] = vis ? depth_key(zv) : KEY_CULLED;
+    vals[i] = i;
+    rects[i] = make_uint2((uint32_t)tr.x0 | ((uint32_t)tr.y0 << 16), (uint32_t)tr.x1 | ((uint32_t)tr.y1 << 16));
+    tcnt[i] = tr.count();   // 4-byte gather target for tile_count_kernel (8 per sector, stays in L2)
   }
-  keys[i] = vis ? depth_key(zv) : KEY_CULLED;
-  vals[i] = i;
-  rects[i] = make_uint2((uint32_t)tr.x0 | ((uint32_t)tr.y0 << 16), (uint32_t)tr.x1 | ((uint32_t)tr.y1 << 16));
-  tcnt[i] = tr.count();   // 4-byte gather target for tile_count_kernel (8 per sector, stays in L2)
+  if (P.stripe_cull) {
+    const int kept = __syncthreads_count(valid && vis);
+    if (threadIdx.x == 0) block_kept[blockIdx.x] = (uint32_t)kept;
+  }
+}
+
+// Stripe renders: squeeze the (depth key, index) pairs of the Gaussians that survived the stripe
+// cull to the front, in index order (the stable sort's tie-break is the input order).  CTA b owns
+// the 256 pairs project_kernel's CTA b wrote; block_off = exclusive scan of block_kept.
+__global__ void __launch_bounds__(256)
+compact_pairs_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                     uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
+                     const uint32_t *__restrict__ block_off, uint32_t n) {
+  __shared__ uint32_t wcnt[8];
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x, lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  uint32_t k = KEY_CULLED, v = 0;
+  if (i < n) { k = keys_in[i]; v = vals_in[i]; }
+  const bool keep = k != KEY_CULLED;
+  const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
+  if (lane == 0) wcnt[w] = __popc(bal);
+  __syncthreads();
+  uint32_t before = 0;
+#pragma unroll
+  for (uint32_t q = 0; q < 8u; ++q) before += (q < w) ? wcnt[q] : 0u;
+  if (keep) {
+    const uint32_t o = block_off[blockIdx.x] + before + __popc(bal & ((1u << lane) - 1u));
+    keys_out[o] = k;
+    vals_out[o] = v;
+  }
 }
 
 }  // namespace splat

@@ -43,6 +43,7 @@ struct splat_ctx {
   uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
   uint2 *rects = nullptr;
   uint32_t *tcnt = nullptr;        // tiles per Gaussian (by Gaussian index)
+  uint32_t *block_kept = nullptr;  // stripe renders: survivors per project CTA, then their exclusive scan
   uint32_t *cnt = nullptr, *offs = nullptr;
   uint32_t *hist = nullptr; size_t hist_cap = 0;
   uint32_t *tot = nullptr;          // 256 digit totals of the current radix pass
@@ -91,21 +92,22 @@ void dev_free(T *&p) {
 inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
 
 // stable LSD radix sort of (key, value) pairs on bits [0, bits); returns the buffer index
-// (0/1) that holds the result
-int radix_sort(splat_ctx *c, cudaStream_t s, uint32_t *keys[2], uint32_t *vals[2], uint32_t n, int bits) {
-  int cur = 0;
+// (0/1) that holds the result.  `n` sizes the grid; if n_ptr is set the kernels sort only the
+// first *n_ptr pairs (a device-side count <= n).
+int radix_sort(splat_ctx *c, cudaStream_t s, uint32_t *keys[2], uint32_t *vals[2], uint32_t n, int bits,
+               int cur = 0, const uint32_t *n_ptr = nullptr) {
   if (n == 0) return cur;
   const uint32_t nblk = cdiv(n, RS_BLOCK);
   for (int shift = 0; shift < bits; shift += 8) {
-    rs_hist_kernel<<<nblk, RS_THREADS, 0, s>>>(keys[cur], nullptr, n, shift, c->hist, nblk);
+    rs_hist_kernel<<<nblk, RS_THREADS, 0, s>>>(keys[cur], n_ptr, n, shift, c->hist, nblk);
     rs_rowscan_kernel<<<256, RW_THREADS, 0, s>>>(c->hist, nblk, c->tot);
     const int nbits = std::min(8, bits - shift);
     if (nbits == 8)
       rs_scatter_kernel<8><<<nblk, RS_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1],
-                                                       nullptr, n, shift, 8, c->hist, c->tot, nblk);
+                                                       n_ptr, n, shift, 8, c->hist, c->tot, nblk);
     else
       rs_scatter_kernel<0><<<nblk, RS_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1],
-                                                       nullptr, n, shift, nbits, c->hist, c->tot, nblk);
+                                                       n_ptr, n, shift, nbits, c->hist, c->tot, nblk);
     c->launches += 3;
     cur ^= 1;
   }
@@ -143,7 +145,7 @@ int ensure_instances(splat_ctx *c, uint64_t want) {
 }
 
 void free_scene(splat_ctx *c) {
-  dev_free(c->scene); dev_free(c->recs); dev_free(c->rects); dev_free(c->tcnt); dev_free(c->cnt); dev_free(c->offs);
+  dev_free(c->scene); dev_free(c->recs); dev_free(c->rects); dev_free(c->tcnt); dev_free(c->block_kept); dev_free(c->cnt); dev_free(c->offs);
   for (int k = 0; k < 2; ++k) { dev_free(c->keys[k]); dev_free(c->vals[k]); }
   c->n = 0;
   c->have_frame = false;
@@ -156,6 +158,7 @@ int alloc_scene(splat_ctx *c, uint64_t n) {
   CU(dev_alloc(&c->recs, n));
   CU(dev_alloc(&c->rects, n));
   CU(dev_alloc(&c->tcnt, n));
+  CU(dev_alloc(&c->block_kept, cdiv(n, 256)));
   CU(dev_alloc(&c->cnt, n));
   CU(dev_alloc(&c->offs, n));
   for (int k = 0; k < 2; ++k) { CU(dev_alloc(&c->keys[k], n)); CU(dev_alloc(&c->vals[k], n)); }
@@ -181,6 +184,7 @@ int make_params(splat_ctx *c, const splat_camera *cam, uint32_t W, uint32_t H, u
   P->sample_off = c->cfg.sample_offset;
   P->ysign = c->cfg.y_down ? 1.0f : -1.0f;
   P->zclip_mode = c->cfg.zclip_mode;
+  P->stripe_cull = (row0 != 0 || row1 != H) ? 1 : 0;
   P->W = W; P->H = H; P->row0 = row0; P->row1 = row1;
   P->tiles_x = cdiv(W, TILE);
   P->tile_y0 = row0 / TILE;
@@ -205,13 +209,26 @@ int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cuda
   c->launches = 0;
   CU(cudaEventRecord(c->ev[EV_START], s));
   CU(cudaMemsetAsync(c->d_status, 0, sizeof(FrameStatus), s));
-  project_kernel<<<cdiv(n, 256), 256, 0, s>>>(c->scene, P, c->recs, c->keys[0], c->vals[0], c->rects, c->tcnt);
+  project_kernel<<<cdiv(n, 256), 256, 0, s>>>(c->scene, P, c->recs, c->keys[0], c->vals[0], c->rects, c->tcnt, c->block_kept);
   c->launches += 1;
   CU(cudaEventRecord(c->ev[EV_PROJECT], s));
-  const int cur = radix_sort(c, s, c->keys, c->vals, n, 32);
+  int cur = 0;
+  const uint32_t *n_sorted = nullptr;
+  if (P.stripe_cull) {
+    // squeeze out what the stripe cannot see, then sort only the survivors (device-side count)
+    const uint32_t nb = cdiv(n, 256), np = std::max(1u, cdiv(nb, SC_BLOCK));
+    scan_reduce_kernel<<<np, SC_THREADS, 0, s>>>(c->block_kept, c->partial, nb);
+    scan_partials_kernel<<<1, 1024, 0, s>>>(c->partial, np, &c->d_status->n_sort);
+    scan_apply_kernel<<<np, SC_THREADS, 0, s>>>(c->block_kept, c->block_kept, c->partial, nb);
+    compact_pairs_kernel<<<nb, 256, 0, s>>>(c->keys[0], c->vals[0], c->keys[1], c->vals[1], c->block_kept, n);
+    c->launches += 4;
+    cur = 1;
+    n_sorted = reinterpret_cast<const uint32_t *>(&c->d_status->n_sort);   // low word (n < 2^31)
+  }
+  cur = radix_sort(c, s, c->keys, c->vals, n, 32, cur, n_sorted);
   c->order_buf = cur;
   CU(cudaEventRecord(c->ev[EV_DSORT], s));
-  tile_count_kernel<<<cdiv(n, 256), 256, 0, s>>>(c->keys[cur], c->vals[cur], c->tcnt, c->cnt, n, c->d_status);
+  tile_count_kernel<<<cdiv(n, 256), 256, 0, s>>>(c->keys[cur], c->vals[cur], c->tcnt, c->cnt, n, n_sorted, c->d_status);
   c->launches += 1;
   // exclusive scan cnt -> offs, grand total -> status.n_instances
   {
@@ -482,7 +499,7 @@ int splat_debug_project(splat_ctx *c, const splat_camera *cam, uint32_t W, uint3
   if (rc) return rc;
   CU(cudaSetDevice(c->cfg.device));
   CU(cudaMemsetAsync(c->recs, 0, (size_t)c->n * sizeof(Rec), c->stream));
-  project_kernel<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->scene, P, c->recs, c->keys[0], c->vals[0], c->rects, c->tcnt);
+  project_kernel<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->scene, P, c->recs, c->keys[0], c->vals[0], c->rects, c->tcnt, c->block_kept);
   CU(cudaGetLastError());
   if (records12) CU(cudaMemcpyAsync(records12, c->recs, (size_t)c->n * sizeof(Rec), cudaMemcpyDeviceToHost, c->stream));
   if (depth_keys) CU(cudaMemcpyAsync(depth_keys, c->keys[0], (size_t)c->n * 4, cudaMemcpyDeviceToHost, c->stream));
