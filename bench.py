@@ -262,8 +262,10 @@ def run_ours(args):
         if world > 1 and not args.equal_stripes:
             ctx.render_device(cam_structs[0], fb_dev.data_ptr(), W, H, 0, H, stream.cuda_stream)
             tl = ctx.tile_loads((W + TILE - 1) // TILE).astype(np.float64)
-            # blend cost of a tile: its list up to the early-termination depth, plus a constant
-            row_load = (np.minimum(tl, 4096.0) + 64.0).sum(axis=1) + 0.35 * tl.sum(axis=1) / 16.0
+            # cost model of a tile in microseconds, from the 1-GPU stage times (profiles/r1l): blend
+            # ~0.4 us per list entry up to the early-termination depth (~280 entries), emit + tile
+            # sort + ranges ~0.016 us per instance, plus a small constant per tile
+            row_load = (0.4 * np.minimum(tl, 280.0) + 0.016 * tl + 2.0).sum(axis=1)
             fb_dev.zero_()
         bounds = stripes.stripe_bounds(H, world, row_load)
     bounds = stripes.broadcast_bounds(bounds, world, dev)
@@ -299,16 +301,25 @@ def run_ours(args):
     inst_sum, launches = 0, 0
     ev0.record(stream)
     for i in range(Wm, Wm + K):
+        frame_device(i)                                 # no per-frame host wait beyond the call's own
+    ev1.record(stream)
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    # per-stage CUDA-event times, work counters and launch counts: the same K frames once more,
+    # untimed, reading the context's stage events after every frame (that read waits for the
+    # frame, which the timed loop above deliberately does not)
+    for i in range(Wm, Wm + K):
         frame_device(i)
         if r1 > r0:
-            tm = ctx.timings()                          # this frame's per-stage CUDA events
+            tm = ctx.timings()
             for k_ in stage:
                 stage[k_] += tm[k_]
             inst_sum += tm["n_instances"]
             launches += tm["kernel_launches"] + 1       # + the clear
-    ev1.record(stream)
     sync_all()
-    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        log(f"[bench] rank {rank}: rows [{r0},{r1}) stage ms/frame " + ", ".join(f"{k_[:-3]} {v / K:.3f}" for k_, v in stage.items())
+            + f", instances/frame {inst_sum / K:.0f}")
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     lsum = torch.tensor([launches], device=dev, dtype=torch.int64)
     if world > 1:
