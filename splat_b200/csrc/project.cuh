@@ -256,10 +256,10 @@ project_kernel(const float4 *__restrict__ scene, const __grid_constant__ FramePa
 
   // power threshold: alpha = min(0.99, op*exp(power)) < 1/255 is certain below pth
   // (0.002 of slack in the exponent against the 1-ulp error of the pinned exp); exp is
-  // flushed to zero below -87, so pth never needs to go lower.
-  float pth;
-  if (!(op > 0.0f)) pth = __int_as_float(0x7f800000);   // never contributes
-  else {
+  // flushed to zero below -87, so pth never needs to go lower.  (double log: only for
+  // Gaussians that are kept)
+  float pth = __int_as_float(0x7f800000);   // never contributes
+  if (vis && op > 0.0f) {
     const double t = log(1.0 / (255.0 * (double)op)) - 2e-3;   // float rounding of t << 2e-3
     pth = (t < -87.0) ? -87.0f : (float)t;
   }

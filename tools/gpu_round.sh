@@ -14,3 +14,9 @@ timeout 900 ncu --set full --clock-control none --import-source on \
     -k regex:"blend_kernel|rs_scatter|rs_hist|emit_instances|tile_count|tile_ranges|project_kernel" -s 68 -c 17 -o gpurun_out/frame_$tag -f \
     python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/ncu_full_$tag.log 2>&1
 ls -la gpurun_out | tail -12
+if [ "${CONFIGS:-0}" = "1" ]; then
+  timeout 900 python tools/configs_report.py 2> gpurun_out/configs_$tag.log | tee gpurun_out/configs_$tag.jsonl | cut -c1-400
+  for n in 100000 1000000; do
+    timeout 300 python bench.py --gaussians $n --steps 20 --warmup 3 2>/dev/null >> gpurun_out/bench_sweep_cpu_$tag.jsonl
+  done
+fi
