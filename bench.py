@@ -360,6 +360,18 @@ def run_ours(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_fps = K / float(e2e_s.item())
     checksum = int(host_np.astype(np.uint64).sum()) if rank == 0 else 0
+    # the same frame through splat_render_cleared (clear folded into the call: no host fill, no
+    # framebuffer upload) -- an optional fast path for callers like main.rs:73-74
+    e2e_cleared = None
+    if world == 1:
+        cl = ctx.L.splat_render_cleared
+        for i in range(Wm):
+            ctx._check(cl(ctx.h, cam_structs[off + i], host_np.ctypes.data, W, H, 0))
+        t_c0 = time.perf_counter()
+        for i in range(Wm, Wm + K):
+            ctx._check(cl(ctx.h, cam_structs[off + i], host_np.ctypes.data, W, H, 0))
+        e2e_cleared = K / (time.perf_counter() - t_c0)
+        assert int(host_np.astype(np.uint64).sum()) == checksum, "splat_render_cleared differs from clear + splat_render"
     if world > 1:
         dsum = int((fb_dev.to(torch.int64) & 0xFFFFFFFF).sum().item())
         log(f"[bench] rank {rank}: device frame checksum {dsum}, own rows "
@@ -386,7 +398,7 @@ def run_ours(args):
             return nbytes / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
 
         # per-stage algorithmic bytes against the same measured HBM peak
-        stage_bytes = {"project_ms": 220.0 * n,                                   # K1: 160 B in + 60 B out per Gaussian
+        stage_bytes = {"project_ms": 228.0 * n,                                   # K1: 160 B in + 68 B out per Gaussian
                        "sort_ms": 20.0 * (4 * n + passes_tile * I),               # K3: 20 B per pair per 8-bit pass
                        "bin_ms": 20.0 * n + 8.0 * I + 4.0 * I + 8.0 * T}          # K2 + K4
         stage_roof = {k_.replace("_ms", ""): {"algorithmic_bytes": b, "ms": ms[k_], "achieved_GBps": gbs(b, ms[k_]),
@@ -399,6 +411,9 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_fps, "unit": "frames/s",
                     "h2d_bytes_per_step": W * H * 4 + 184, "d2h_bytes_per_step": W * H * 4 + 16},
+            "e2e_cleared": None if e2e_cleared is None else
+            {"value": e2e_cleared, "unit": "frames/s", "h2d_bytes_per_step": 184, "d2h_bytes_per_step": W * H * 4 + 16,
+             "call": "splat_render_cleared (device-side clear instead of a host fill + upload)"},
             "gpu_launches": int(lsum.item()),
             "roofline": {"kernel": "blend_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

@@ -116,6 +116,12 @@ int splat_upload_aos(splat_ctx *ctx, const float *gaussians59, uint64_t n);
  * camera.h == H (true for every caller in the reference). */
 int splat_render(splat_ctx *ctx, const splat_camera *cam, uint32_t *fb_inout, uint32_t W, uint32_t H);
 
+/* `color = Buffer2d::fill([W, H], clear); render_to_buffer(&mut color)` in one call (what
+ * main.rs:73-74 does every frame with clear = 0): the frame is cleared on the device, so the
+ * caller neither fills the host buffer nor pays its upload; fb_out is only written. */
+int splat_render_cleared(splat_ctx *ctx, const splat_camera *cam, uint32_t *fb_out, uint32_t W, uint32_t H,
+                         uint32_t clear);
+
 /* Same for a horizontal stripe of rows [row0,row1) of the W x H image (multi-GPU sharding by
  * screen-tile stripes): fb_rows points at row row0 and holds (row1-row0)*W pixels.  row0 must
  * be a multiple of the tile size; row1 a multiple of it or == H. */

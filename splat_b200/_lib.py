@@ -18,7 +18,7 @@ ERRORS = {-1: "SPLAT_ERR_INVALID", -2: "SPLAT_ERR_CUDA", -3: "SPLAT_ERR_NOMEM",
 
 # every symbol include/splat.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = ["splat_abi_version", "splat_config_default", "splat_create", "splat_destroy",
-           "splat_last_error", "splat_upload_soa", "splat_upload_aos", "splat_render",
+           "splat_last_error", "splat_upload_soa", "splat_upload_aos", "splat_render", "splat_render_cleared",
            "splat_render_rows", "splat_render_device", "splat_get_timings", "splat_get_tile_loads", "splat_pin_host",
            "splat_unpin_host", "splat_debug_project", "splat_debug_read_order",
            "splat_debug_sort_pairs", "splat_debug_blend_stats"]
@@ -77,6 +77,7 @@ def load():
     L.splat_upload_soa.argtypes = [vp, fp, fp, fp, fp, fp, C.c_uint64]
     L.splat_upload_aos.argtypes = [vp, fp, C.c_uint64]
     L.splat_render.argtypes = [vp, C.POINTER(SplatCamera), vp, C.c_uint32, C.c_uint32]
+    L.splat_render_cleared.argtypes = [vp, C.POINTER(SplatCamera), vp, C.c_uint32, C.c_uint32, C.c_uint32]
     L.splat_render_rows.argtypes = [vp, C.POINTER(SplatCamera), vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     L.splat_render_device.argtypes = [vp, C.POINTER(SplatCamera), vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp]
     L.splat_get_timings.argtypes = [vp, C.POINTER(SplatTimings)]
@@ -158,6 +159,13 @@ class Context:
         row1 = H if row1 is None else row1
         assert fb.shape == (row1 - row0, W)
         self._check(self.L.splat_render_rows(self.h, C.byref(cam), fb.ctypes.data, W, H, row0, row1))
+
+    def render_cleared(self, cam: SplatCamera, fb: np.ndarray, clear: int = 0):
+        """clear + render_to_buffer in one call; fb (H, W) uint32 is only written."""
+        assert fb.dtype == np.uint32 and fb.flags["C_CONTIGUOUS"]
+        H, W = int(cam.h), int(cam.w)
+        assert fb.shape == (H, W)
+        self._check(self.L.splat_render_cleared(self.h, C.byref(cam), fb.ctypes.data, W, H, clear))
 
     def render_ptr(self, cam: SplatCamera, host_ptr: int, W: int, H: int, row0=0, row1=None):
         self._check(self.L.splat_render_rows(self.h, C.byref(cam), host_ptr, W, H, row0, H if row1 is None else row1))

@@ -196,6 +196,13 @@ int make_params(splat_ctx *c, const splat_camera *cam, uint32_t W, uint32_t H, u
   return SPLAT_OK;
 }
 
+__global__ void __launch_bounds__(256) fill_u32_kernel(uint32_t *p, uint32_t v, size_t n) {
+  const size_t i0 = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (i0 + k < n) p[i0 + k] = v;
+}
+
 int ilog2_ceil(uint32_t v) {
   int b = 0;
   while ((1ull << b) < v) ++b;
@@ -445,6 +452,39 @@ int splat_render_rows(splat_ctx *c, const splat_camera *cam, uint32_t *fb_rows, 
 
 int splat_render(splat_ctx *c, const splat_camera *cam, uint32_t *fb, uint32_t W, uint32_t H) {
   return splat_render_rows(c, cam, fb, W, H, 0, H);
+}
+
+int splat_render_cleared(splat_ctx *c, const splat_camera *cam, uint32_t *fb_out, uint32_t W, uint32_t H,
+                         uint32_t clear) {
+  if (!c) return SPLAT_ERR_INVALID;
+  if (!c->n) return fail(c, SPLAT_ERR_STATE, "no scene uploaded");
+  if (!fb_out) return fail(c, SPLAT_ERR_INVALID, "framebuffer is null");
+  FrameParams P;
+  int rc = make_params(c, cam, W, H, 0, H, &P);
+  if (rc) return rc;
+  CU(cudaSetDevice(c->cfg.device));
+  const size_t px = (size_t)W * H;
+  if (px > c->fb_cap) {
+    CU(cudaStreamSynchronize(c->stream));
+    dev_free(c->d_fb);
+    CU(dev_alloc(&c->d_fb, px));
+    c->fb_cap = px;
+  }
+  CU(cudaEventRecord(c->ev[EV_H2D0], c->stream));
+  if (clear == 0u || ((clear & 0xFFu) * 0x01010101u) == clear) {
+    CU(cudaMemsetAsync(c->d_fb, (int)(clear & 0xFFu), px * 4, c->stream));
+  } else {
+    fill_u32_kernel<<<cdiv(px, 1024), 256, 0, c->stream>>>(c->d_fb, clear, px);
+  }
+  CU(cudaEventRecord(c->ev[EV_H2D1], c->stream));
+  rc = render_frame(c, P, c->d_fb, c->stream, nullptr);
+  if (rc) return rc;
+  CU(cudaEventRecord(c->ev[EV_D2H0], c->stream));
+  CU(cudaMemcpyAsync(fb_out, c->d_fb, px * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaEventRecord(c->ev[EV_D2H1], c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->host_copy = true;
+  return SPLAT_OK;
 }
 
 int splat_get_timings(splat_ctx *c, splat_timings *t) {

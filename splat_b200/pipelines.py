@@ -44,6 +44,18 @@ class _PipelineBase:
         cam = _lib.camera_struct(self.camera)
         self._ctx._check(self._ctx.L.splat_render(self._ctx.h, cam, color.ctypes.data, W, H))
 
+    def render_cleared_to_buffer(self, color: np.ndarray, clear: int = 0) -> None:
+        """`color.fill(clear); render_to_buffer(color)` (main.rs:73-74) without the host fill and
+        its upload: `color` is only written."""
+        if color.dtype != np.uint32 or color.ndim != 2 or not color.flags["C_CONTIGUOUS"]:
+            raise TypeError("color must be a C-contiguous (H, W) uint32 array")
+        if self._uploaded is not self.gaussians:
+            self._upload()
+            self._uploaded = self.gaussians
+        H, W = color.shape
+        cam = _lib.camera_struct(self.camera)
+        self._ctx._check(self._ctx.L.splat_render_cleared(self._ctx.h, cam, color.ctypes.data, W, H, clear))
+
     def timings(self) -> dict:
         return self._ctx.timings()
 

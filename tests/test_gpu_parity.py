@@ -257,6 +257,24 @@ def test_degenerate_inputs_are_skipped(lib, orc):
     assert np.array_equal(fb, ref)
 
 
+def test_render_cleared_equals_fill_then_render(lib, orc):
+    """splat_render_cleared == Buffer2d::fill(clear) + render_to_buffer (main.rs:73-74), for a
+    byte-uniform and a general clear value, whatever the output buffer held before."""
+    W, H = 333, 200
+    scene = _scene(5_000, 0x5EED0034, -3.2)
+    cam = _camera(W, H, (0.0, 0.0, 4.5), yaw=0.2)
+    ctx = lib.Context(device=0)
+    ctx.upload(scene)
+    cs = lib.camera_struct(cam)
+    for clear in (0, 0x7F7F7F7F, 0x00336699):
+        want = np.full((H, W), clear, np.uint32)
+        orc.render(scene, orc.camera_from(cam), orc.make_config(), want)
+        got = np.random.default_rng(9).integers(0, 2 ** 32, size=(H, W), dtype=np.uint64).astype(np.uint32)
+        ctx.render_cleared(cs, got, clear)
+        assert np.array_equal(got, want), hex(clear)
+    ctx.close()
+
+
 def test_pipeline_mirrors(lib, orc):
     """The reference-shaped entry points: Pipeline01 (AoS, low-pass 0.01) and Pipeline02 (SoA, 0.3)
     on the reference's own 4-Gaussian scene and 01_naive_gaussian.rs-like setup."""
