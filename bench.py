@@ -180,7 +180,7 @@ def run_reference(args):
     scene = make_scene(n)
     cov3d = orc.compute_cov3d(scene.rotations, scene.scales)   # once per scene, like main.rs:24-26
     cams = orbit_cameras(W, H, args.warmup + args.steps)
-    row_step = args.cpu_row_step or 16
+    row_step = args.cpu_row_step or 4      # same bounded sample as the cpu_baseline leg of the GPU arm
     times, last = [], None
     for i, camt in enumerate(cams):
         last = cpu_frame_time(orc, scene, cov3d, camt, W, H, row_step, cores)
