@@ -44,7 +44,7 @@
 // framebuffer contents.  The kernel therefore composites only a SUFFIX of the tile list, carrying
 // two states per pixel (started at 0 and at 255) until they coincide for all pixels of the group
 // and one state afterwards; if some pixel has not converged when the list ends the attempt is
-// repeated with a 4x longer suffix, and an attempt that reaches the head of the list starts from
+// repeated with a 2x longer suffix, and an attempt that reaches the head of the list starts from
 // the real framebuffer bytes (the plain algorithm).  On the 6.1M-Gaussian bench scene a pixel is
 // covered by ~1,800 contributing entries of which the last ~100 decide its value.
 //
@@ -64,12 +64,12 @@ constexpr int BL_BATCH = 256;                      // list entries staged per ro
 constexpr int BL_CH = 8;                           // list entries per ring chunk
 constexpr int BL_SLOTS = 16;                       // ring chunk slots per CTA, split among the unit's groups
 #ifndef SPLAT_SUFFIX0
-#define SPLAT_SUFFIX0 256
+#define SPLAT_SUFFIX0 192
 #endif
 #ifndef SPLAT_SUFFIX_GROWTH
-#define SPLAT_SUFFIX_GROWTH 4
+#define SPLAT_SUFFIX_GROWTH 2
 #endif
-constexpr uint32_t BL_SUFFIX0 = SPLAT_SUFFIX0;              // list entries composited by the first suffix attempt
+constexpr uint32_t BL_SUFFIX0 = SPLAT_SUFFIX0;              // list entries composited by the first suffix attempt (r1q/r1r sweeps)
 constexpr uint32_t BL_SUFFIX_GROWTH = SPLAT_SUFFIX_GROWTH;  // growth factor per failed attempt
 constexpr uint32_t BL_SUFFIX_MIN_LEN = 3 * BL_SUFFIX0 / 2;  // shorter lists are composited whole, straight away
 
@@ -381,7 +381,7 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
   // extreme states (byte 0 and byte 255).  Each entry's byte -> byte map is monotone, so once
   // the two trajectories of a pixel coincide the result no longer depends on anything earlier
   // in the list -- or on the framebuffer contents.  If some pixel has not converged when the
-  // list ends, the attempt is repeated with a 4x longer suffix; an attempt that reaches the
+  // list ends, the attempt is repeated with a 2x longer suffix; an attempt that reaches the
   // head of the list starts from the real framebuffer bytes and is exact by construction.
   uint32_t start = range.x;
   bool exact = true;
