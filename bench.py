@@ -229,7 +229,12 @@ def run_ours(args):
         # NCCL prints its version banner on stdout; stdout carries exactly one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
-    _lib.load()   # raises if libsplat_b200.so is missing: no CPU fallback
+    if not os.path.exists(_lib.LIB_PATH) and local == 0:
+        import __graft_entry__ as g   # fresh checkout: compile with nvcc; there is no CPU fallback
+        g.build()
+    if world > 1:
+        dist.barrier()
+    _lib.load()   # raises if libsplat_b200.so is still missing
 
     W, H, n = args.width, args.height, args.n
     K, Wm = args.steps, args.warmup

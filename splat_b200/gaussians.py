@@ -255,3 +255,33 @@ def load_ply_soa(filename: str) -> GaussianList:
         avg = np.array([np.cumsum(pos[:, k], dtype=f32)[-1] for k in range(3)], f32) / f32(n)
         pos[:, :3] = pos[:, :3] - avg
     return GaussianList(pos, scales, opac, rot, sh)
+
+
+def trim_ply(src: str, dst: str, count: int = 3) -> int:
+    """`trim` (src/bin/00_ply_load.rs:9-63): copy the first `count` vertices of a binary
+    little-endian PLY into a new PLY with the same header otherwise (tiny test scenes).  Returns
+    the number of vertices written."""
+    with open(src, "rb") as f:
+        data = f.read()
+    end = data.index(b"end_header\n") + len(b"end_header\n")
+    lines = data[:end].decode("ascii").split("\n")
+    sizes = {"float": 4, "float32": 4, "double": 8, "float64": 8, "uchar": 1, "uint8": 1, "char": 1,
+             "short": 2, "ushort": 2, "int": 4, "uint": 4}
+    n, stride, out_lines = 0, 0, []
+    for ln in lines:
+        t = ln.split()
+        if len(t) == 3 and t[0] == "element":
+            if t[1] != "vertex":
+                raise ValueError("Unexpected element!")
+            n = int(t[2])
+            ln = f"element vertex {min(n, count)}"
+        elif len(t) == 3 and t[0] == "property":
+            stride += sizes[t[1]]
+        elif len(t) >= 2 and t[0] == "format" and t[1] != "binary_little_endian":
+            raise ValueError("trim_ply handles binary_little_endian files")
+        out_lines.append(ln)
+    m = min(n, count)
+    with open(dst, "wb") as f:
+        f.write("\n".join(out_lines).encode("ascii"))
+        f.write(data[end:end + m * stride])
+    return m

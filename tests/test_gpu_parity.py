@@ -9,8 +9,14 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def lib():
+    import os
+
     from splat_b200 import _lib
 
+    if not os.path.exists(_lib.LIB_PATH):     # fresh checkout: compile (nvcc), never fall back
+        import __graft_entry__ as g
+
+        g.build()
     _lib.load()
     return _lib
 

@@ -67,3 +67,18 @@ def test_unexpected_element_is_an_error(tmp_path):
     p.write_bytes(b"ply\nformat binary_little_endian 1.0\nelement face 0\nend_header\n")
     with pytest.raises(ValueError):
         load_ply_soa(str(p))                             # gaussians.rs:390 panics
+
+
+def test_trim_keeps_the_first_vertices(tmp_path):
+    """`trim` (00_ply_load.rs): first three vertices, same schema."""
+    from splat_b200.gaussians import load_ply_soa, save_ply, trim_ply
+
+    raw = _raw(10, seed=3)
+    src, dst = str(tmp_path / "a.ply"), str(tmp_path / "b.ply")
+    save_ply(src, raw)
+    assert trim_ply(src, dst, 3) == 3
+    a, b = load_ply_soa(src), load_ply_soa(dst)
+    assert b.num_gaussians == 3
+    # activations are per vertex; only the recentring (mean over the file) differs
+    assert np.array_equal(a.scales[:3], b.scales[:3]) and np.array_equal(a.sh[:3], b.sh[:3])
+    assert np.array_equal(a.opacities[:3], b.opacities[:3]) and np.array_equal(a.rotations[:3], b.rotations[:3])
