@@ -144,6 +144,8 @@ rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
     const uint32_t li = w * RS_WARP_SPAN + k * 32 + lane;
     const bool valid = li < nvalid;
     const uint32_t d = (key[k] >> shift) & 0xFFu;
+    // (mixing in a few match.any rounds to run on the ADU pipe beside the ballots was tried
+    // and is slower: r1s)
     uint32_t peers = __ballot_sync(0xFFFFFFFFu, valid);
     const int nb = NB ? NB : nbits;
 #pragma unroll
