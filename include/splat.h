@@ -58,7 +58,9 @@ typedef struct {
   uint32_t tile;           /* screen tile edge in pixels; only 16 is built                       */
   uint64_t max_instances;  /* initial capacity of the tile-instance buffers (0 = auto, grows)    */
   int32_t  blend_mode;     /* SPLAT_BLEND_*: 0 = the reference's quantised far->near blend (parity) */
-  int32_t  reserved;       /* must be 0                                                          */
+  int32_t  near_cut;       /* first bin + sort only the nearest k/1024 of the Gaussians and fall back to all
+                            * of them when a pixel does not converge (results identical either way):
+                            * 0 = automatic (starts at 1/8, doubles after a fall-back), -1 = off, 1..1024 = fixed */
 } splat_config;
 
 /* What the kernels need from `Camera` (camera.rs:4-19): the two matrices exactly as nalgebra
@@ -82,13 +84,16 @@ typedef struct {
   float    total_ms;     /* first kernel to last kernel                        */
   float    h2d_ms;       /* framebuffer upload (host-buffer entry points only) */
   float    d2h_ms;       /* framebuffer download                               */
-  uint32_t frames_retried; /* renders repeated because the instance buffers had to grow */
+  uint32_t frames_retried; /* renders (partly) repeated: instance buffers had to grow, or a near-cut pass did not converge */
   uint64_t n_gaussians;
   uint64_t n_visible;    /* Gaussians that pass the z clip and the degeneracy guard (stripe renders:
                           * and whose quad can touch the stripe -- the others are dropped before the sort) */
   uint64_t n_instances;  /* (tile, Gaussian) pairs                                  */
   uint64_t n_tiles;      /* tiles in the rendered stripe                            */
   uint64_t kernel_launches; /* kernels launched by the last render                  */
+  uint64_t near_cut_rank;   /* depth ranks below this were left out of the first binning pass (0 = none);
+                             * frames_retried also counts the renders that then needed the complete pass */
+  uint64_t near_cut_failed; /* pixel groups / tiles that did not converge in that pass (0 = it was enough) */
 } splat_timings;
 
 uint32_t    splat_abi_version(void);

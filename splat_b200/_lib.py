@@ -27,7 +27,7 @@ EXPORTS = ["splat_abi_version", "splat_config_default", "splat_create", "splat_d
 class SplatConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("lowpass", C.c_float), ("y_down", C.c_int32),
                 ("zclip_mode", C.c_int32), ("sample_offset", C.c_float), ("tile", C.c_uint32),
-                ("max_instances", C.c_uint64), ("blend_mode", C.c_int32), ("reserved", C.c_int32)]
+                ("max_instances", C.c_uint64), ("blend_mode", C.c_int32), ("near_cut", C.c_int32)]
 
 
 class SplatCamera(C.Structure):
@@ -41,7 +41,7 @@ class SplatTimings(C.Structure):
                 ("blend_ms", C.c_float), ("total_ms", C.c_float), ("h2d_ms", C.c_float),
                 ("d2h_ms", C.c_float), ("frames_retried", C.c_uint32),
                 ("n_gaussians", C.c_uint64), ("n_visible", C.c_uint64), ("n_instances", C.c_uint64),
-                ("n_tiles", C.c_uint64), ("kernel_launches", C.c_uint64)]
+                ("n_tiles", C.c_uint64), ("kernel_launches", C.c_uint64), ("near_cut_rank", C.c_uint64), ("near_cut_failed", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -118,12 +118,13 @@ def _fp(a):
 class Context:
     """Owns one splat_ctx (one GPU)."""
 
-    def __init__(self, device=0, lowpass=0.3, y_down=1, zclip_mode=0, sample_offset=0.5, max_instances=0):
+    def __init__(self, device=0, lowpass=0.3, y_down=1, zclip_mode=0, sample_offset=0.5, max_instances=0, near_cut=0):
         self.L = load()
         cfg = SplatConfig()
         self.L.splat_config_default(C.byref(cfg))
         cfg.device, cfg.lowpass, cfg.y_down = device, lowpass, y_down
         cfg.zclip_mode, cfg.sample_offset, cfg.max_instances = zclip_mode, sample_offset, max_instances
+        cfg.near_cut = near_cut
         self.cfg = cfg
         self.h = C.c_void_p()
         rc = self.L.splat_create(C.byref(self.h), C.byref(cfg))

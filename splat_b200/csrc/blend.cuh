@@ -274,9 +274,24 @@ SPLAT_DEVINL void producers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(BL_PRO
 // different SMs with 4 (8) producer warps per group.  Empty tiles produce no unit.
 SPLAT_DEVINL uint32_t unit_split(uint32_t len, uint32_t t2, uint32_t t4) { return len > t4 ? 4u : (len > t2 ? 2u : 1u); }
 
+// near cut: grow the bounding box (in stripe-local tile coordinates) of the tiles that need the
+// complete lists
+SPLAT_DEVINL void mark_failed_tile(FrameStatus *status, uint32_t *tile_failed, uint32_t tile, uint32_t tx, uint32_t ty) {
+  tile_failed[tile] = 1u;
+  atomicMax(&status->fail_ix0, ~tx);
+  atomicMax(&status->fail_iy0, ~ty);
+  atomicMax(&status->fail_x1, tx);
+  atomicMax(&status->fail_y1, ty);
+}
+
 __global__ void __launch_bounds__(1024)
 unit_order_kernel(const uint2 *__restrict__ ranges, uint32_t T, uint2 *__restrict__ units,
-                  uint32_t *__restrict__ n_units, const unsigned long long *__restrict__ n_instances) {
+                  uint32_t *__restrict__ n_units, const unsigned long long *__restrict__ n_instances,
+                  const uint32_t *__restrict__ far_cnt, FrameStatus *__restrict__ status, uint32_t tiles_x,
+                  uint32_t *__restrict__ tile_failed, int only_failed) {
+  // only_failed: the pass after a near-cut pass blends nothing but the tiles that pass marked --
+  // every other tile is final, and one that was composited from the framebuffer bytes must not
+  // be composited onto its own output again
   constexpr int NB = 512;
   __shared__ uint32_t hist[NB];
   for (int i = threadIdx.x; i < NB; i += blockDim.x) hist[i] = 0;
@@ -292,10 +307,17 @@ unit_order_kernel(const uint2 *__restrict__ ranges, uint32_t T, uint2 *__restric
     const int b = (int)(16.0f * __log2f((float)len));   // 0 .. 16*32-1
     return (uint32_t)max(0, NB - 1 - b);
   };
+  uint32_t lost = 0;   // near cut: tiles whose whole list was cut away get no unit -- the frame needs the full lists
   for (uint32_t t = threadIdx.x; t < T; t += blockDim.x) {
     const uint2 r = ranges[t];
+    if (only_failed && !tile_failed[t]) continue;
     if (r.y > r.x) atomicAdd(&hist[bucket(r.y - r.x)], unit_split(r.y - r.x, t2, t4));
+    else if (far_cnt && far_cnt[t]) {
+      lost += 1;
+      mark_failed_tile(status, tile_failed, t, t % tiles_x, t / tiles_x);
+    }
   }
+  if (lost) atomicAdd(&status->n_failed, lost);
   __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t run = 0;
@@ -306,6 +328,7 @@ unit_order_kernel(const uint2 *__restrict__ ranges, uint32_t T, uint2 *__restric
   for (uint32_t t = threadIdx.x; t < T; t += blockDim.x) {
     const uint2 r = ranges[t];
     if (r.y <= r.x) continue;
+    if (only_failed && !tile_failed[t]) continue;
     const uint32_t nu = unit_split(r.y - r.x, t2, t4), ng = 4u / nu;
     const uint32_t pos = atomicAdd(&hist[bucket(r.y - r.x)], nu);
     for (uint32_t k = 0; k < nu; ++k) units[pos + k] = make_uint2(t, ng | ((k * ng) << 8));
@@ -333,6 +356,7 @@ struct BlendSmem {
   uint32_t wcount[BL_GROUPS][BL_PRODUCER_THREADS / 32];   // per staging warp, per group
   uint8_t list[BL_GROUPS][BL_BATCH];                      // compacted entry indices per group
   uint32_t fail[BL_GROUPS];                               // per team: the suffix attempt did not converge
+  uint32_t giveup;                                        // truncated list with a pixel nothing covers
 };
 constexpr size_t BL_SMEM_BYTES = sizeof(BlendSmem);
 
@@ -355,7 +379,8 @@ SPLAT_DEVINL float fragment_alpha(float sx, float sy, const float4 a, const floa
 __global__ void __launch_bounds__(BL_THREADS, 3)
 blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
              const uint32_t *__restrict__ n_units, const uint32_t *__restrict__ inst_vals, const Rec *__restrict__ recs,
-             uint32_t *__restrict__ fb_rows, const __grid_constant__ FrameParams P) {
+             uint32_t *__restrict__ fb_rows, const __grid_constant__ FrameParams P,
+             const uint32_t *__restrict__ far_cnt, FrameStatus *__restrict__ status, uint32_t *__restrict__ tile_failed) {
   extern __shared__ __align__(16) unsigned char blend_smem_raw[];
   BlendSmem &S = *reinterpret_cast<BlendSmem *>(blend_smem_raw);
 
@@ -375,6 +400,13 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
   const f32x2 NZ = P.nz2;
   const uint32_t len = range.y - range.x;
   uint32_t suffix = BL_SUFFIX0;
+  // near cut (bin.cuh): Gaussians farther than everything in this list were not binned this pass
+  // and some of them touch this tile.  The list is then only a suffix of the real one: it can
+  // never be composited "exactly from its head"; if its pixels do not converge the frame is
+  // repeated with the full lists (splat_api.cu).
+  const bool truncated = far_cnt != nullptr && far_cnt[tile] != 0u;
+  bool gave_up = false;
+  if (tid == 0) S.giveup = 0;
 
   // ---- suffix attempts (see "Exact early termination" in the header) ----
   // Attempt k composites only the last `suffix` list entries, starting every pixel from BOTH
@@ -391,8 +423,9 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
   bool alpha_done = false;
 
   for (;;) {
-  exact = (len <= BL_SUFFIX_MIN_LEN) || (suffix >= len);
-  start = exact ? range.x : range.y - suffix;
+  const bool whole = (len <= BL_SUFFIX_MIN_LEN) || (suffix >= len);
+  exact = whole && !truncated;
+  start = whole ? range.x : range.y - suffix;
   if (tid < BL_SLOTS) {
     mbar_init(&S.full[tid], 1);
     mbar_init(&S.empty[tid], 1);
@@ -700,7 +733,13 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
       if (lane == 0) mbar_arrive(&S.empty[slot]);
       if (h & 0x100u) break;
     }
-    if (lane == 0) S.fail[gl] = dual ? 1u : 0u;
+    // truncated list: an inside pixel that none of its quads covers may be covered by a cut one
+    const bool unknown = truncated && __any_sync(0xFFFFFFFFu, (inside0 && last0 == 0xFFFFFFFFu) ||
+                                                                 (inside1 && last1 == 0xFFFFFFFFu));
+    if (lane == 0) {
+      S.fail[gl] = (dual || unknown) ? 1u : 0u;
+      if (unknown) S.giveup = 1u;
+    }
 #ifdef SPLAT_STATS
     if (lane == 0) { STAT_ADD(6, 1); STAT_ADD(7, dual ? 1 : 0); }
 #endif
@@ -710,6 +749,7 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
   uint32_t any_fail = 0;
   for (uint32_t q = 0; q < ng; ++q) any_fail |= S.fail[q];
   if (!any_fail) break;
+  if (whole || S.giveup) { gave_up = true; break; }     // only possible for a truncated list
   suffix = (suffix > 0x10000000u) ? 0xFFFFFFFFu : suffix * BL_SUFFIX_GROWTH;
   if (tid < BL_SLOTS) {
     mbar_inval(&S.full[tid]);
@@ -717,8 +757,13 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
   }
   }   // attempts
 
-  if (w >= BL_PRODUCER_THREADS / 32) {
+  if (gave_up && tid == 0) {
+    atomicAdd(&status->n_failed, 1u);
+    mark_failed_tile(status, tile_failed, tile, tile_x, tile_y);
+  }
+  if (w >= BL_PRODUCER_THREADS / 32 && !(gave_up && S.fail[w - BL_PRODUCER_THREADS / 32])) {
     // epilogue: pack RGB, resolve the alpha byte (E7), write the pixel
+    // (a group of a given-up unit that did converge still writes: its values are final)
     const uint32_t g = g0 + (w - BL_PRODUCER_THREADS / 32);
     const uint32_t px = tx0 + 8u * (g & 1u) + (lane & 7u);
     const uint32_t py0 = ty0 + 8u * (g >> 1) + (lane >> 3), py1 = py0 + 4u;

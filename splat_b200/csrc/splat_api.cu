@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -26,6 +27,9 @@
 using namespace splat;
 
 namespace {
+constexpr uint64_t NEAR_CUT_MIN_VISIBLE = 200000;   // smaller scenes: the cut's own kernels cost more than they save
+constexpr size_t FAR_SMEM_MAX = 200 * 1024;            // difference array of far_cover_kernel (shared memory)
+constexpr uint32_t NEAR_CUT_DEFAULT = 128;             // 1/8 of the Gaussians
 enum { EV_START = 0, EV_PROJECT, EV_DSORT, EV_COUNT, EV_EMIT, EV_TSORT, EV_RANGES, EV_BLEND,
        EV_H2D0, EV_H2D1, EV_D2H0, EV_D2H1, EV_COUNT_ };
 }
@@ -52,6 +56,12 @@ struct splat_ctx {
   uint32_t *ikeys[2] = {nullptr, nullptr}, *ivals[2] = {nullptr, nullptr};
   uint2 *ranges = nullptr; size_t ranges_cap = 0;
   uint2 *units = nullptr;          // blend work units, heaviest first (up to 4 per tile)
+  uint32_t *far_cnt = nullptr;     // near cut: cut Gaussians per tile
+  uint32_t *tile_failed = nullptr; // near cut: tiles that need the complete lists
+  int *far_diff = nullptr;         // its 2-D difference array
+  uint32_t cut_frac = 1024;        // Gaussians binned by the near-cut pass, in 1/1024 (1024 = no cut)
+  uint32_t last_cut = 0;           // rank_cut of the last frame
+  uint32_t last_failed = 0;        // groups / tiles that did not converge in its near-cut pass
   uint32_t *n_units = nullptr;
   FrameStatus *d_status = nullptr, *h_status = nullptr;
   uint32_t *d_fb = nullptr; size_t fb_cap = 0;
@@ -209,6 +219,101 @@ int ilog2_ceil(uint32_t v) {
   return std::max(b, 1);
 }
 
+// Second half of a frame on `s`: bin the Gaussians of depth rank >= rank_cut into tiles, sort the
+// instances by tile, blend.  rank_cut = 0 is the complete frame; rank_cut > 0 is the near-cut
+// pass (bin.cuh), after which h_status->n_failed says whether the complete pass must follow.
+int render_back(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cudaStream_t s, cudaEvent_t wait_ev,
+                int cur, const uint32_t *n_sorted, uint32_t rank_cut, const TileRect *only_box = nullptr, bool only_failed = false) {
+  TileRect box;                      // tiles this pass bins into (stripe-local tile coordinates)
+  box.x0 = 0; box.y0 = 0; box.x1 = 0xFFFF; box.y1 = 0xFFFF;
+  if (only_box) box = *only_box;
+  const uint32_t n = c->n;
+  const uint32_t T = P.tiles_x * P.tiles_y;
+  if (T > c->ranges_cap) {
+    dev_free(c->ranges);
+    dev_free(c->units);
+    dev_free(c->far_cnt);
+    dev_free(c->far_diff);
+    dev_free(c->tile_failed);
+    CU(dev_alloc(&c->ranges, T));
+    CU(dev_alloc(&c->units, (size_t)4 * T));
+    CU(dev_alloc(&c->far_cnt, T));
+    CU(dev_alloc(&c->tile_failed, T));
+    CU(dev_alloc(&c->far_diff, (size_t)(P.tiles_x + 1) * (P.tiles_y + 1)));
+    c->ranges_cap = T;
+  }
+  // n_instances, n_visible, n_failed (n_sort, behind them, belongs to the first half)
+  CU(cudaMemsetAsync(c->d_status, 0, offsetof(FrameStatus, n_sort), s));
+  const uint32_t *far = nullptr;
+  if (rank_cut) {
+    const size_t cells = (size_t)(P.tiles_x + 1) * (P.tiles_y + 1);
+    CU(cudaMemsetAsync(c->far_diff, 0, cells * sizeof(int), s));
+    CU(cudaMemsetAsync(c->tile_failed, 0, (size_t)T * sizeof(uint32_t), s));
+    far_cover_kernel<<<148, FC_THREADS, cells * sizeof(int), s>>>(c->vals[cur], c->rects, n_sorted, n, rank_cut,
+                                                                  P.tiles_x, P.tiles_y, c->far_diff);
+    far_prefix_kernel<<<1, 1024, cells * sizeof(int), s>>>(c->far_diff, P.tiles_x, P.tiles_y, c->far_cnt);
+    c->launches += 2;
+    far = c->far_cnt;
+  }
+  tile_count_kernel<<<cdiv(n, 256), 256, 0, s>>>(c->keys[cur], c->vals[cur], c->tcnt, c->cnt, n, n_sorted, rank_cut, c->d_status,
+                                                  only_box ? c->rects : nullptr, box);
+  c->launches += 1;
+  // exclusive scan cnt -> offs, grand total -> status.n_instances
+  {
+    const uint32_t np = std::max(1u, cdiv(n, SC_BLOCK));
+    scan_reduce_kernel<<<np, SC_THREADS, 0, s>>>(c->cnt, c->partial, n);
+    scan_partials_kernel<<<1, 1024, 0, s>>>(c->partial, np, &c->d_status->n_instances);
+    scan_apply_kernel<<<np, SC_THREADS, 0, s>>>(c->cnt, c->offs, c->partial, n);
+    c->launches += 3;
+  }
+  CU(cudaEventRecord(c->ev[EV_COUNT], s));
+  CU(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(FrameStatus), cudaMemcpyDeviceToHost, s));
+  CU(cudaEventRecord(c->status_ev, s));
+  CU(cudaEventSynchronize(c->status_ev));   // host round trip: the instance count sizes the next launches
+  const uint64_t I = c->h_status->n_instances;
+  c->last_instances = I;
+  c->last_visible = c->h_status->n_visible;
+  c->last_tiles = (uint64_t)T;
+  if (I > c->inst_cap) {
+    int rc = ensure_instances(c, I);
+    if (rc) return rc;
+    c->retried += 1;
+  }
+  int icur = 0;
+  if (I > 0) {
+    emit_instances_kernel<<<cdiv(n, 256), 256, 0, s>>>(c->vals[cur], c->rects, c->cnt, c->offs,
+                                                        c->ikeys[0], c->ivals[0], n, P.tiles_x, box);
+    c->launches += 1;
+  }
+  CU(cudaEventRecord(c->ev[EV_EMIT], s));
+  if (I > 0) icur = radix_sort(c, s, c->ikeys, c->ivals, (uint32_t)I, ilog2_ceil(T));
+  CU(cudaEventRecord(c->ev[EV_TSORT], s));
+  CU(cudaMemsetAsync(c->ranges, 0, (size_t)T * sizeof(uint2), s));
+  if (I > 0) {
+    tile_ranges_kernel<<<cdiv(I, 1024), 256, 0, s>>>(c->ikeys[icur], (uint32_t)I, c->ranges);
+    c->launches += 1;
+  }
+  if (I > 0 || far) {
+    unit_order_kernel<<<1, 1024, 0, s>>>(c->ranges, T, c->units, c->n_units, &c->d_status->n_instances, far, c->d_status, P.tiles_x,
+                                         c->tile_failed, only_failed ? 1 : 0);   // heaviest first
+    c->launches += 1;
+  }
+  CU(cudaEventRecord(c->ev[EV_RANGES], s));
+  if (wait_ev) CU(cudaStreamWaitEvent(s, wait_ev, 0));
+  if (I > 0) {
+    blend_kernel<<<4 * T, BL_THREADS, BL_SMEM_BYTES, s>>>(c->ranges, c->units, c->n_units, c->ivals[icur], c->recs, fb_rows_dev, P,
+                                                          far, c->d_status, c->tile_failed);
+    c->launches += 1;
+  }
+  CU(cudaEventRecord(c->ev[EV_BLEND], s));
+  if (rank_cut) {
+    CU(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(FrameStatus), cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(c->status_ev, s));
+    CU(cudaEventSynchronize(c->status_ev));   // did every pixel converge on the near lists?
+  }
+  return SPLAT_OK;
+}
+
 // Enqueue one frame on `s`, writing rows [row0,row1) into fb_rows_dev.  If wait_ev is set the
 // blend kernel waits for it (framebuffer upload on the copy stream).
 int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cudaStream_t s, cudaEvent_t wait_ev) {
@@ -235,59 +340,42 @@ int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cuda
   cur = radix_sort(c, s, c->keys, c->vals, n, 32, cur, n_sorted);
   c->order_buf = cur;
   CU(cudaEventRecord(c->ev[EV_DSORT], s));
-  tile_count_kernel<<<cdiv(n, 256), 256, 0, s>>>(c->keys[cur], c->vals[cur], c->tcnt, c->cnt, n, n_sorted, c->d_status);
-  c->launches += 1;
-  // exclusive scan cnt -> offs, grand total -> status.n_instances
-  {
-    const uint32_t np = std::max(1u, cdiv(n, SC_BLOCK));
-    scan_reduce_kernel<<<np, SC_THREADS, 0, s>>>(c->cnt, c->partial, n);
-    scan_partials_kernel<<<1, 1024, 0, s>>>(c->partial, np, &c->d_status->n_instances);
-    scan_apply_kernel<<<np, SC_THREADS, 0, s>>>(c->cnt, c->offs, c->partial, n);
-    c->launches += 3;
+
+  // Near cut: the blend reads only the nearest few hundred entries of every tile list (exact early
+  // termination), so first bin + sort only the nearest cut_frac/1024 of the Gaussians -- the
+  // depth ranks the previous frame makes us expect at the top -- and fall back to the complete
+  // lists only if some pixel did not converge on them (then keep twice as many from now on).
+  uint32_t rank_cut = 0;
+  const size_t far_smem = (size_t)(P.tiles_x + 1) * (P.tiles_y + 1) * sizeof(int);
+  const uint64_t min_visible = c->cfg.near_cut > 0 ? 1u : NEAR_CUT_MIN_VISIBLE;   // a fixed fraction is honoured on any scene (tests)
+  if (c->cut_frac < 1024u && c->have_frame && c->last_visible >= min_visible && far_smem <= FAR_SMEM_MAX) {
+    const uint64_t keep = (c->last_visible * c->cut_frac + 1023u) / 1024u;
+    if (keep < c->last_visible) rank_cut = (uint32_t)(c->last_visible - keep);
   }
-  CU(cudaEventRecord(c->ev[EV_COUNT], s));
-  CU(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(FrameStatus), cudaMemcpyDeviceToHost, s));
-  CU(cudaEventRecord(c->status_ev, s));
-  CU(cudaEventSynchronize(c->status_ev));   // the frame's only host round trip
-  const uint64_t I = c->h_status->n_instances;
-  c->last_instances = I;
-  c->last_visible = c->h_status->n_visible;
-  c->last_tiles = (uint64_t)P.tiles_x * P.tiles_y;
-  if (I > c->inst_cap) {
-    int rc = ensure_instances(c, I);
-    if (rc) return rc;
+  int rc = render_back(c, P, fb_rows_dev, s, wait_ev, cur, n_sorted, rank_cut);
+  if (rc) return rc;
+  c->last_cut = rank_cut;
+  c->last_failed = rank_cut ? c->h_status->n_failed : 0u;
+  if (rank_cut && (c->h_status->n_failed != 0 || c->h_status->n_instances == 0)) {
+    // The near lists were not enough for this view: bin + sort + blend again with ALL Gaussians,
+    // restricted to the bounding box of the tiles that did not converge when that box is small
+    // (typically a strip along one screen edge).  Groups that already converged wrote final values
+    // and, if they are blended again, converge to them again without reading the framebuffer;
+    // groups that did not converge left their pixels untouched.
+    const FrameStatus fs = *c->h_status;
+    TileRect fbx;
+    fbx.x0 = (uint16_t)~fs.fail_ix0; fbx.y0 = (uint16_t)~fs.fail_iy0;
+    fbx.x1 = (uint16_t)fs.fail_x1;   fbx.y1 = (uint16_t)fs.fail_y1;
+    const bool have_box = fs.n_failed != 0 && fs.n_instances != 0 && fbx.x1 >= fbx.x0 && fbx.y1 >= fbx.y0;
+    const uint64_t area = have_box ? (uint64_t)(fbx.x1 - fbx.x0 + 1) * (fbx.y1 - fbx.y0 + 1) : ~0ull;
+    const bool partial = have_box && area * 2u <= (uint64_t)P.tiles_x * P.tiles_y;
+    if (!partial && c->cfg.near_cut == 0) c->cut_frac = std::min<uint32_t>(1024u, c->cut_frac * 2u);
     c->retried += 1;
+    const uint64_t near_instances = fs.n_instances;
+    rc = render_back(c, P, fb_rows_dev, s, wait_ev, cur, n_sorted, 0, partial ? &fbx : nullptr, fs.n_instances != 0);
+    if (rc) return rc;
+    if (partial) c->last_instances += near_instances;     // both passes' instances were binned and sorted
   }
-  const uint32_t T = P.tiles_x * P.tiles_y;
-  if (T > c->ranges_cap) {
-    dev_free(c->ranges);
-    dev_free(c->units);
-    CU(dev_alloc(&c->ranges, T));
-    CU(dev_alloc(&c->units, (size_t)4 * T));
-    c->ranges_cap = T;
-  }
-  int icur = 0;
-  if (I > 0) {
-    emit_instances_kernel<<<cdiv(n, 256), 256, 0, s>>>(c->vals[cur], c->rects, c->cnt, c->offs,
-                                                        c->ikeys[0], c->ivals[0], n, P.tiles_x);
-    c->launches += 1;
-  }
-  CU(cudaEventRecord(c->ev[EV_EMIT], s));
-  if (I > 0) icur = radix_sort(c, s, c->ikeys, c->ivals, (uint32_t)I, ilog2_ceil(T));
-  CU(cudaEventRecord(c->ev[EV_TSORT], s));
-  CU(cudaMemsetAsync(c->ranges, 0, (size_t)T * sizeof(uint2), s));
-  if (I > 0) {
-    tile_ranges_kernel<<<cdiv(I, 1024), 256, 0, s>>>(c->ikeys[icur], (uint32_t)I, c->ranges);
-    unit_order_kernel<<<1, 1024, 0, s>>>(c->ranges, T, c->units, c->n_units, &c->d_status->n_instances);   // heaviest first
-    c->launches += 2;
-  }
-  CU(cudaEventRecord(c->ev[EV_RANGES], s));
-  if (wait_ev) CU(cudaStreamWaitEvent(s, wait_ev, 0));
-  if (I > 0) {
-    blend_kernel<<<4 * T, BL_THREADS, BL_SMEM_BYTES, s>>>(c->ranges, c->units, c->n_units, c->ivals[icur], c->recs, fb_rows_dev, P);
-    c->launches += 1;
-  }
-  CU(cudaEventRecord(c->ev[EV_BLEND], s));
   CU(cudaGetLastError());
   c->have_frame = true;
   return SPLAT_OK;
@@ -314,7 +402,7 @@ void splat_config_default(splat_config *cfg) {
   cfg->tile = TILE;
   cfg->max_instances = 0;
   cfg->blend_mode = SPLAT_BLEND_REFERENCE;
-  cfg->reserved = 0;
+  cfg->near_cut = 0;
 }
 
 int splat_create(splat_ctx **out, const splat_config *cfg) {
@@ -326,6 +414,8 @@ int splat_create(splat_ctx **out, const splat_config *cfg) {
   auto bail = [&](int code) { splat_destroy(c); return code; };
   if (c->cfg.tile != (uint32_t)TILE) return bail(SPLAT_ERR_UNSUPPORTED);
   if (c->cfg.blend_mode != SPLAT_BLEND_REFERENCE) return bail(SPLAT_ERR_UNSUPPORTED);
+  if (c->cfg.near_cut < -1 || c->cfg.near_cut > 1024) return bail(SPLAT_ERR_INVALID);
+  c->cut_frac = c->cfg.near_cut == 0 ? NEAR_CUT_DEFAULT : (c->cfg.near_cut < 0 ? 1024u : (uint32_t)c->cfg.near_cut);
   if (!(c->cfg.lowpass >= 0.0f) || !std::isfinite(c->cfg.sample_offset)) return bail(SPLAT_ERR_INVALID);
   if (cudaSetDevice(c->cfg.device) != cudaSuccess) return bail(SPLAT_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(SPLAT_ERR_CUDA);
@@ -335,6 +425,10 @@ int splat_create(splat_ctx **out, const splat_config *cfg) {
   if (cudaEventCreateWithFlags(&c->status_ev, cudaEventDisableTiming) != cudaSuccess) return bail(SPLAT_ERR_CUDA);
   if (cudaEventCreateWithFlags(&c->h2d_done, cudaEventDisableTiming) != cudaSuccess) return bail(SPLAT_ERR_CUDA);
   if (cudaFuncSetAttribute(blend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BL_SMEM_BYTES) != cudaSuccess)
+    return bail(SPLAT_ERR_CUDA);
+  if (cudaFuncSetAttribute(far_cover_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAR_SMEM_MAX) != cudaSuccess)
+    return bail(SPLAT_ERR_CUDA);
+  if (cudaFuncSetAttribute(far_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAR_SMEM_MAX) != cudaSuccess)
     return bail(SPLAT_ERR_CUDA);
   if (dev_alloc(&c->d_status, 1) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
   if (dev_alloc(&c->n_units, 1) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
@@ -349,7 +443,7 @@ void splat_destroy(splat_ctx *c) {
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_scene(c);
-  dev_free(c->hist); dev_free(c->tot); dev_free(c->partial); dev_free(c->ranges); dev_free(c->units); dev_free(c->n_units); dev_free(c->d_status); dev_free(c->d_fb);
+  dev_free(c->hist); dev_free(c->tot); dev_free(c->partial); dev_free(c->ranges); dev_free(c->units); dev_free(c->far_cnt); dev_free(c->far_diff); dev_free(c->tile_failed); dev_free(c->n_units); dev_free(c->d_status); dev_free(c->d_fb);
   for (int k = 0; k < 2; ++k) { dev_free(c->ikeys[k]); dev_free(c->ivals[k]); }
   if (c->h_status) cudaFreeHost(c->h_status);
   for (int i = 0; i < EV_COUNT_; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -510,6 +604,8 @@ int splat_get_timings(splat_ctx *c, splat_timings *t) {
   t->n_instances = c->last_instances;
   t->n_tiles = c->last_tiles;
   t->kernel_launches = c->launches;
+  t->near_cut_rank = c->last_cut;
+  t->near_cut_failed = c->last_failed;
   return SPLAT_OK;
 }
 

@@ -182,6 +182,65 @@ def test_deep_lists_exact_early_termination(lib, orc, case):
     assert np.array_equal(fb, ref), f"{np.count_nonzero(fb != ref)} of {W*H} pixels differ"
 
 
+@pytest.mark.parametrize("frac,expect_fallback", [(512, False), (128, None), (16, None), (1, True)])
+def test_near_cut_is_exact(lib, orc, frac, expect_fallback):
+    """Near cut: the second and later frames of a context first bin + sort only the nearest
+    frac/1024 of the Gaussians; tiles whose pixels do not converge on those make the frame fall
+    back to the complete lists.  Either way the pixels must equal the oracle's -- on a noise
+    framebuffer, so that a wrongly skipped far Gaussian or a wrongly kept input byte shows."""
+    W, H = 160, 96
+    scene = _scene(200_000, 0x5EED0054, -2.8)
+    scene.opacities[::3] = 0.02          # some faint ones so that convergence needs depth
+    ctx = lib.Context(device=0, near_cut=frac)
+    ctx.upload(scene)
+    cfg = orc.make_config()
+    retried0 = None
+    for k, yaw in enumerate((0.0, 0.3, 0.6)):
+        cam = _camera(W, H, (0.0, 0.0, 2.5), yaw=yaw)
+        fb0 = np.random.default_rng(100 + k).integers(0, 2 ** 32, size=(H, W), dtype=np.uint64).astype(np.uint32)
+        ref = fb0.copy()
+        orc.render(scene, orc.camera_from(cam), cfg, ref)
+        got = fb0.copy()
+        ctx.render(lib.camera_struct(cam), got)
+        t = ctx.timings()
+        assert np.array_equal(got, ref), f"frame {k}: {np.count_nonzero(got != ref)} pixels differ"
+        if k == 0:
+            assert t["near_cut_rank"] == 0      # no previous frame to size the cut from
+            retried0 = t["frames_retried"]
+        else:
+            assert t["near_cut_rank"] > 0
+    fell_back = t["frames_retried"] > retried0
+    if expect_fallback is not None:
+        assert fell_back == expect_fallback
+    ctx.close()
+
+
+def test_near_cut_stripes_and_empty_regions(lib, orc):
+    """Near cut with a stripe render and with screen regions nothing covers (tiles whose list is
+    empty both before and after the cut must not trigger the fall-back, tiles whose list the cut
+    emptied must)."""
+    W, H = 320, 200
+    scene = _scene(60_000, 0x5EED0055, -4.0)
+    rng = np.random.default_rng(55)
+    scene.positions[:, :3] = rng.normal(0.0, 0.25, size=(60_000, 3)).astype(np.float32)
+    scene.positions[:, 0] -= 1.0                                    # a small blob on one side, nothing elsewhere
+    cam = _camera(W, H, (0.0, 0.0, 3.0))
+    want = np.zeros((H, W), np.uint32)
+    orc.render(scene, orc.camera_from(cam), orc.make_config(), want)
+    assert np.count_nonzero(want == 0) > W * H // 10
+    for frac in (256, 8):
+        ctx = lib.Context(device=0, near_cut=frac)
+        ctx.upload(scene)
+        for rep in range(2):
+            got = np.zeros((H, W), np.uint32)
+            for r0, r1 in ((0, 96), (96, 200)):
+                part = np.ascontiguousarray(got[r0:r1])
+                ctx.render(lib.camera_struct(cam), part, r0, r1)
+                got[r0:r1] = part
+            assert np.array_equal(got, want), (frac, rep, int(np.count_nonzero(got != want)))
+        ctx.close()
+
+
 @pytest.mark.parametrize("y_down,zclip", [(0, 0), (1, 1), (0, 2)])
 def test_euc_switches(lib, orc, y_down, zclip):
     W, H = 400, 300

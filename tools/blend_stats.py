@@ -24,9 +24,10 @@ def main():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--frames", type=int, default=3)
+    ap.add_argument("--near-cut", type=int, default=0)
     a = ap.parse_args()
     sc = bench.make_scene(a.n)
-    ctx = _lib.Context(device=0, lowpass=bench.LOWPASS)
+    ctx = _lib.Context(device=0, lowpass=bench.LOWPASS, near_cut=a.near_cut)
     ctx.upload(sc)
     cams = bench.orbit_cameras(a.width, a.height, a.frames)
     fb = np.zeros((a.height, a.width), np.uint32)
@@ -39,7 +40,8 @@ def main():
         t = ctx.timings()
         st = ctx.debug_blend_stats(reset=True)
         d = {k: int(v) for k, v in zip(names, st)}
-        d.update(frame=i, n_instances=int(t["n_instances"]), n_visible=int(t["n_visible"]), blend_ms=t["blend_ms"])
+        d.update(frame=i, n_instances=int(t["n_instances"]), n_visible=int(t["n_visible"]), blend_ms=t["blend_ms"],
+                 near_cut_rank=int(t["near_cut_rank"]), near_cut_failed=int(t["near_cut_failed"]), frames_retried=int(t["frames_retried"]), total_ms=t["total_ms"])
         d["lane_fill_consumer"] = d["lanes_alpha_gt0"] / max(1, 32 * d["group_entries_to_consumer"])
         d["lane_fill_producer"] = d["lanes_alpha_gt0"] / max(1, 32 * d["group_entries_evaluated"])
         print(json.dumps(d), flush=True)
