@@ -94,6 +94,7 @@ typedef struct {
   uint64_t near_cut_rank;   /* depth ranks below this were left out of the first binning pass (0 = none);
                              * frames_retried also counts the renders that then needed the complete pass */
   uint64_t near_cut_failed; /* pixel groups / tiles that did not converge in that pass (0 = it was enough) */
+  uint64_t near_cut_instances; /* (tile, Gaussian) pairs that pass did not have to bin and sort */
 } splat_timings;
 
 uint32_t    splat_abi_version(void);

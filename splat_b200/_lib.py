@@ -41,7 +41,7 @@ class SplatTimings(C.Structure):
                 ("blend_ms", C.c_float), ("total_ms", C.c_float), ("h2d_ms", C.c_float),
                 ("d2h_ms", C.c_float), ("frames_retried", C.c_uint32),
                 ("n_gaussians", C.c_uint64), ("n_visible", C.c_uint64), ("n_instances", C.c_uint64),
-                ("n_tiles", C.c_uint64), ("kernel_launches", C.c_uint64), ("near_cut_rank", C.c_uint64), ("near_cut_failed", C.c_uint64)]
+                ("n_tiles", C.c_uint64), ("kernel_launches", C.c_uint64), ("near_cut_rank", C.c_uint64), ("near_cut_failed", C.c_uint64), ("near_cut_instances", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -104,7 +104,8 @@ far_cover_kernel(const uint32_t *__restrict__ order, const uint2 *__restrict__ r
 // Single CTA: 2-D inclusive prefix sum of the difference array (in shared memory) ->
 // far_cnt[ty * tiles_x + tx].
 __global__ void __launch_bounds__(1024)
-far_prefix_kernel(const int *__restrict__ diff, uint32_t tiles_x, uint32_t tiles_y, uint32_t *__restrict__ far_cnt) {
+far_prefix_kernel(const int *__restrict__ diff, uint32_t tiles_x, uint32_t tiles_y, uint32_t *__restrict__ far_cnt,
+                  FrameStatus *__restrict__ status) {
   extern __shared__ int s_diff[];
   const uint32_t pitch = tiles_x + 1u, cells = pitch * (tiles_y + 1u);
   for (uint32_t i = threadIdx.x; i < cells; i += blockDim.x) s_diff[i] = diff[i];
@@ -119,8 +120,14 @@ far_prefix_kernel(const int *__restrict__ diff, uint32_t tiles_x, uint32_t tiles
     for (uint32_t y = 0; y < tiles_y; ++y) { run += s_diff[y * pitch + x]; s_diff[y * pitch + x] = run; }
   }
   __syncthreads();
-  for (uint32_t i = threadIdx.x; i < tiles_x * tiles_y; i += blockDim.x)
-    far_cnt[i] = (uint32_t)s_diff[(i / tiles_x) * pitch + (i % tiles_x)];
+  unsigned long long cut = 0;
+  for (uint32_t i = threadIdx.x; i < tiles_x * tiles_y; i += blockDim.x) {
+    const uint32_t v = (uint32_t)s_diff[(i / tiles_x) * pitch + (i % tiles_x)];
+    far_cnt[i] = v;
+    cut += v;
+  }
+  for (int o = 16; o > 0; o >>= 1) cut += __shfl_xor_sync(0xFFFFFFFFu, cut, o);
+  if ((threadIdx.x & 31u) == 0 && cut) atomicAdd(&status->n_cut, cut);
 }
 
 // Duplication, load-balanced over OUTPUT positions: a CTA owns 256 consecutive depth ranks, whose

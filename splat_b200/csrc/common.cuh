@@ -51,6 +51,7 @@ struct FrameStatus {
   unsigned int n_failed;           // near-cut frames: groups / tiles whose pixels need Gaussians that were cut
   unsigned int fail_ix0, fail_iy0; // bounding box of those tiles: ~min x, ~min y (kept as maxima so that 0 = none)
   unsigned int fail_x1, fail_y1;   //                             max x, max y
+  unsigned long long n_cut;        // near-cut frames: (tile, Gaussian) pairs that were not binned
   unsigned long long n_sort;       // stripe renders: (key, index) pairs that enter the depth sort
 };
 

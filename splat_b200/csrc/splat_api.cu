@@ -62,6 +62,7 @@ struct splat_ctx {
   uint32_t cut_frac = 1024;        // Gaussians binned by the near-cut pass, in 1/1024 (1024 = no cut)
   uint32_t last_cut = 0;           // rank_cut of the last frame
   uint32_t last_failed = 0;        // groups / tiles that did not converge in its near-cut pass
+  uint64_t last_cut_instances = 0; // (tile, Gaussian) pairs it did not bin
   uint32_t *n_units = nullptr;
   FrameStatus *d_status = nullptr, *h_status = nullptr;
   uint32_t *d_fb = nullptr; size_t fb_cap = 0;
@@ -251,7 +252,7 @@ int render_back(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cudaS
     CU(cudaMemsetAsync(c->tile_failed, 0, (size_t)T * sizeof(uint32_t), s));
     far_cover_kernel<<<148, FC_THREADS, cells * sizeof(int), s>>>(c->vals[cur], c->rects, n_sorted, n, rank_cut,
                                                                   P.tiles_x, P.tiles_y, c->far_diff);
-    far_prefix_kernel<<<1, 1024, cells * sizeof(int), s>>>(c->far_diff, P.tiles_x, P.tiles_y, c->far_cnt);
+    far_prefix_kernel<<<1, 1024, cells * sizeof(int), s>>>(c->far_diff, P.tiles_x, P.tiles_y, c->far_cnt, c->d_status);
     c->launches += 2;
     far = c->far_cnt;
   }
@@ -356,6 +357,7 @@ int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cuda
   if (rc) return rc;
   c->last_cut = rank_cut;
   c->last_failed = rank_cut ? c->h_status->n_failed : 0u;
+  c->last_cut_instances = rank_cut ? c->h_status->n_cut : 0ull;
   if (rank_cut && (c->h_status->n_failed != 0 || c->h_status->n_instances == 0)) {
     // The near lists were not enough for this view: bin + sort + blend again with ALL Gaussians,
     // restricted to the bounding box of the tiles that did not converge when that box is small
@@ -606,6 +608,7 @@ int splat_get_timings(splat_ctx *c, splat_timings *t) {
   t->kernel_launches = c->launches;
   t->near_cut_rank = c->last_cut;
   t->near_cut_failed = c->last_failed;
+  t->near_cut_instances = c->last_cut_instances;
   return SPLAT_OK;
 }
 
