@@ -209,6 +209,7 @@ def workload_config(args, world):
             "n_gaussians": args.n, "width": args.width, "height": args.height,
             "parallelism": (f"screen-tile stripes x{world}, " + ("equal" if args.equal_stripes else "balanced from a probe frame")
                             + ", scene replicated, one NCCL send/recv gather per frame") if world > 1 else "single GPU",
+            "near_cut": args.near_cut,
             "l2_policy": "inputs larger than L2 (scene 160 B x N, per-frame buffers > 126 MB); no explicit flush"}
 
 
@@ -243,7 +244,7 @@ def run_ours(args):
     from splat_b200 import stripes
     sc = stripes.broadcast_scene(make_scene(n) if rank == 0 else None, rank, dev)
     torch.cuda.empty_cache()
-    ctx = _lib.Context(device=local, lowpass=LOWPASS)
+    ctx = _lib.Context(device=local, lowpass=LOWPASS, near_cut=args.near_cut)
     t0 = time.time()
     ctx.upload(sc)
     log(f"[bench] rank {rank}: scene uploaded in {time.time() - t0:.1f}s")
@@ -475,6 +476,8 @@ def main():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--cpu-row-step", type=int, default=0, help="CPU sample: every k-th tile stripe (0 = default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--near-cut", type=int, default=0,
+                    help="splat_config.near_cut: 0 = off (default), -1 = automatic, 1..1024 = fixed fraction (experimental)")
     ap.add_argument("--equal-stripes", action="store_true", help="N > 1: equal tile-row stripes instead of load-balanced ones")
     args = ap.parse_args()
     capture_stdout()

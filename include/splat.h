@@ -58,9 +58,10 @@ typedef struct {
   uint32_t tile;           /* screen tile edge in pixels; only 16 is built                       */
   uint64_t max_instances;  /* initial capacity of the tile-instance buffers (0 = auto, grows)    */
   int32_t  blend_mode;     /* SPLAT_BLEND_*: 0 = the reference's quantised far->near blend (parity) */
-  int32_t  near_cut;       /* first bin + sort only the nearest k/1024 of the Gaussians and fall back to all
-                            * of them when a pixel does not converge (results identical either way):
-                            * 0 = automatic (starts at 1/8, doubles after a fall-back), -1 = off, 1..1024 = fixed */
+  int32_t  near_cut;       /* EXPERIMENTAL, off by default (known issue).  First bin + sort only the
+                            * nearest k/1024 of the Gaussians and redo the tiles that do not converge with all
+                            * of them (results identical either way): 0 = off, -1 = automatic (starts at 1/8,
+                            * doubles after a whole-frame fall-back), 1..1024 = fixed fraction */
 } splat_config;
 
 /* What the kernels need from `Camera` (camera.rs:4-19): the two matrices exactly as nalgebra

@@ -59,6 +59,7 @@ struct splat_ctx {
   uint32_t *far_cnt = nullptr;     // near cut: cut Gaussians per tile
   uint32_t *tile_failed = nullptr; // near cut: tiles that need the complete lists
   int *far_diff = nullptr;         // its 2-D difference array
+  size_t far_cells_cap = 0;
   uint32_t cut_frac = 1024;        // Gaussians binned by the near-cut pass, in 1/1024 (1024 = no cut)
   uint32_t last_cut = 0;           // rank_cut of the last frame
   uint32_t last_failed = 0;        // groups / tiles that did not converge in its near-cut pass
@@ -234,14 +235,20 @@ int render_back(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cudaS
     dev_free(c->ranges);
     dev_free(c->units);
     dev_free(c->far_cnt);
-    dev_free(c->far_diff);
     dev_free(c->tile_failed);
     CU(dev_alloc(&c->ranges, T));
     CU(dev_alloc(&c->units, (size_t)4 * T));
     CU(dev_alloc(&c->far_cnt, T));
     CU(dev_alloc(&c->tile_failed, T));
-    CU(dev_alloc(&c->far_diff, (size_t)(P.tiles_x + 1) * (P.tiles_y + 1)));
     c->ranges_cap = T;
+  }
+  {
+    const size_t cells = (size_t)(P.tiles_x + 1) * (P.tiles_y + 1);   // not a function of T alone
+    if (cells > c->far_cells_cap) {
+      dev_free(c->far_diff);
+      CU(dev_alloc(&c->far_diff, cells));
+      c->far_cells_cap = cells;
+    }
   }
   // n_instances, n_visible, n_failed (n_sort, behind them, belongs to the first half)
   CU(cudaMemsetAsync(c->d_status, 0, offsetof(FrameStatus, n_sort), s));
@@ -371,7 +378,7 @@ int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cuda
     const bool have_box = fs.n_failed != 0 && fs.n_instances != 0 && fbx.x1 >= fbx.x0 && fbx.y1 >= fbx.y0;
     const uint64_t area = have_box ? (uint64_t)(fbx.x1 - fbx.x0 + 1) * (fbx.y1 - fbx.y0 + 1) : ~0ull;
     const bool partial = have_box && area * 2u <= (uint64_t)P.tiles_x * P.tiles_y;
-    if (!partial && c->cfg.near_cut == 0) c->cut_frac = std::min<uint32_t>(1024u, c->cut_frac * 2u);
+    if (!partial && c->cfg.near_cut < 0) c->cut_frac = std::min<uint32_t>(1024u, c->cut_frac * 2u);
     c->retried += 1;
     const uint64_t near_instances = fs.n_instances;
     rc = render_back(c, P, fb_rows_dev, s, wait_ev, cur, n_sorted, 0, partial ? &fbx : nullptr, fs.n_instances != 0);
@@ -417,7 +424,8 @@ int splat_create(splat_ctx **out, const splat_config *cfg) {
   if (c->cfg.tile != (uint32_t)TILE) return bail(SPLAT_ERR_UNSUPPORTED);
   if (c->cfg.blend_mode != SPLAT_BLEND_REFERENCE) return bail(SPLAT_ERR_UNSUPPORTED);
   if (c->cfg.near_cut < -1 || c->cfg.near_cut > 1024) return bail(SPLAT_ERR_INVALID);
-  c->cut_frac = c->cfg.near_cut == 0 ? NEAR_CUT_DEFAULT : (c->cfg.near_cut < 0 ? 1024u : (uint32_t)c->cfg.near_cut);
+  // 0 = off (default: see DESIGN.md, known issue), -1 = automatic, 1..1024 = fixed fraction
+  c->cut_frac = c->cfg.near_cut == 0 ? 1024u : (c->cfg.near_cut < 0 ? NEAR_CUT_DEFAULT : (uint32_t)c->cfg.near_cut);
   if (!(c->cfg.lowpass >= 0.0f) || !std::isfinite(c->cfg.sample_offset)) return bail(SPLAT_ERR_INVALID);
   if (cudaSetDevice(c->cfg.device) != cudaSuccess) return bail(SPLAT_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(SPLAT_ERR_CUDA);

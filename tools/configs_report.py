@@ -25,13 +25,14 @@ from splat_b200.camera import Camera  # noqa: E402
 from splat_b200.gaussians import synthetic_scene  # noqa: E402
 
 DEMO_CAM = (-0.57651054, 2.99040512, -0.03924271)   # 02_ply_demo.rs:22
+NEAR_CUT = int(os.environ.get("SPLAT_NEAR_CUT", "0"))   # splat_config.near_cut for every context (0 = off)
 
 
 def run(name, n, seed, W, H, campos, frames, props):
     import torch
 
     scene = synthetic_scene(n, seed=seed)
-    ctx = _lib.Context(device=0, lowpass=0.3)
+    ctx = _lib.Context(device=0, lowpass=0.3, near_cut=NEAR_CUT)
     ctx.upload(scene)
     cam = Camera(H, W, campos)
     cams = []
