@@ -52,8 +52,10 @@ enum {
 typedef struct {
   int32_t  device;         /* CUDA device ordinal                                                */
   float    lowpass;        /* 0.01 = Pipeline01 (gaussians.rs:156-157), 0.3 = Pipeline02 (:517-518) */
-  int32_t  y_down;         /* 1: NDC +y is the bottom row (euc CoordinateMode::VULKAN default)    */
-  int32_t  zclip_mode;     /* 0: keep 0<=z<1, 1: keep -1<=z<1, 2: no z clip                       */
+  int32_t  y_down;         /* 0 (default): NDC +y is the TOP row -- what the reference's own images show
+                            * (notes/screenshot.png and notebook cells 3/6, pinned by
+                            * tests/test_reference_images.py); 1: NDC +y is the bottom row          */
+  int32_t  zclip_mode;     /* 0: keep 0<=z<1, 1 (default, goes with y-up): keep -1<=z<1, 2: no z clip */
   float    sample_offset;  /* pixel sample point (x+off, y+off); 0.5                             */
   uint32_t tile;           /* screen tile edge in pixels; only 16 is built                       */
   uint64_t max_instances;  /* initial capacity of the tile-instance buffers (0 = auto, grows)    */

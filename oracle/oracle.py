@@ -82,6 +82,9 @@ def lib():
                                  C.c_uint32, C.c_uint32, C.POINTER(OrcStats)]
         L.orc_shade_blend.restype = C.c_uint32
         L.orc_shade_blend.argtypes = [C.c_uint32] + [C.c_float] * 6 + [fp, C.c_int]
+        L.orc_render_float.restype = C.c_int
+        L.orc_render_float.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(OrcConfig), C.c_void_p,
+                                       C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]
         L.orc_sizeof_splat.restype = C.c_uint32
         assert L.orc_sizeof_splat() == SPLAT_DTYPE.itemsize == C.sizeof(OrcSplat)
         _lib = L
@@ -115,7 +118,7 @@ def camera_from(camera) -> OrcCamera:
                        camera.w, camera.h, hf[0], hf[1], hf[2])
 
 
-def make_config(lowpass=0.3, y_down=1, zclip_mode=0, sample_offset=0.5, exp_mode=0,
+def make_config(lowpass=0.3, y_down=0, zclip_mode=1, sample_offset=0.5, exp_mode=0,
                 nthreads=None) -> OrcConfig:
     if nthreads is None:
         nthreads = os.cpu_count() or 1
@@ -191,6 +194,21 @@ def render(scene, cam: OrcCamera, cfg: OrcConfig, fb: np.ndarray, row0=0, row1=N
     if rc:
         raise RuntimeError(f"orc_render failed: {rc}")
     return st
+
+
+def render_float(splats, order, cfg: OrcConfig, rgb: np.ndarray, acc_alpha: np.ndarray | None = None, mode: int = 0):
+    """Un-quantised back-to-front "over" compositing onto rgb ((H, W, 3) f32) in place.
+    mode 0 = the Rust fragment() semantics (pixel-centre sampling, 1/255 alpha cut, unclamped colour);
+    mode 1 = the prototype's plot_opacity (notebook cell 3) restated line by line."""
+    H, W, ch = rgb.shape
+    assert ch == 3 and rgb.dtype == np.float32 and rgb.flags["C_CONTIGUOUS"]
+    if acc_alpha is not None:
+        assert acc_alpha.shape == (H, W) and acc_alpha.dtype == np.float32 and acc_alpha.flags["C_CONTIGUOUS"]
+    order = np.ascontiguousarray(order, np.uint32)
+    rc = lib().orc_render_float(splats.ctypes.data, order.ctypes.data, len(order), C.byref(cfg), rgb.ctypes.data,
+                                acc_alpha.ctypes.data if acc_alpha is not None else None, W, H, int(mode))
+    if rc:
+        raise RuntimeError(f"orc_render_float failed: {rc}")
 
 
 def shade_blend(old: int, A, B, Cc, dx, dy, opacity, rgb, exp_mode=0) -> int:

@@ -118,7 +118,7 @@ def _fp(a):
 class Context:
     """Owns one splat_ctx (one GPU)."""
 
-    def __init__(self, device=0, lowpass=0.3, y_down=1, zclip_mode=0, sample_offset=0.5, max_instances=0, near_cut=0):
+    def __init__(self, device=0, lowpass=0.3, y_down=0, zclip_mode=1, sample_offset=0.5, max_instances=0, near_cut=0):
         self.L = load()
         cfg = SplatConfig()
         self.L.splat_config_default(C.byref(cfg))

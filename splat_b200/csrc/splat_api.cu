@@ -405,8 +405,8 @@ void splat_config_default(splat_config *cfg) {
   if (!cfg) return;
   cfg->device = 0;
   cfg->lowpass = 0.3f;        // Pipeline02 (gaussians.rs:517-518)
-  cfg->y_down = 1;
-  cfg->zclip_mode = 0;
+  cfg->y_down = 0;            // E1: pinned by the reference's own images (tests/test_reference_images.py)
+  cfg->zclip_mode = 1;
   cfg->sample_offset = 0.5f;
   cfg->tile = TILE;
   cfg->max_instances = 0;

@@ -22,8 +22,8 @@ from .gaussians import Gaussian, GaussianList
 class _PipelineBase:
     LOWPASS = 0.3
 
-    def __init__(self, gaussians, camera: Camera, device: int = 0, y_down: int = 1,
-                 zclip_mode: int = 0, sample_offset: float = 0.5):
+    def __init__(self, gaussians, camera: Camera, device: int = 0, y_down: int = 0,
+                 zclip_mode: int = 1, sample_offset: float = 0.5):
         self.gaussians = gaussians
         self.camera = camera
         self._ctx = _lib.Context(device=device, lowpass=self.LOWPASS, y_down=y_down,

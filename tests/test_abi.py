@@ -49,7 +49,7 @@ def test_abi_version_and_defaults(lib):
     assert L.splat_abi_version() == int(re.search(r"SPLAT_ABI_VERSION\s+(\d+)u", open(HEADER).read()).group(1))
     cfg = lib.SplatConfig()
     L.splat_config_default(C.byref(cfg))
-    assert cfg.device == 0 and cfg.tile == 16 and cfg.y_down == 1 and cfg.zclip_mode == 0
+    assert cfg.device == 0 and cfg.tile == 16 and cfg.y_down == 0 and cfg.zclip_mode == 1
     assert np.float32(cfg.lowpass) == np.float32(0.3) and cfg.sample_offset == 0.5   # Pipeline02
 
 

@@ -42,7 +42,7 @@ def _scene(n, seed, log_scale_mean=-4.0):
 DEMO_CAM = (-0.57651054, 2.99040512, -0.03924271)   # 02_ply_demo.rs:22
 
 
-def _render_both(lib, orc, scene, cam, W, H, lowpass=0.3, y_down=1, zclip_mode=0, fb0=None, rows=None):
+def _render_both(lib, orc, scene, cam, W, H, lowpass=0.3, y_down=0, zclip_mode=1, fb0=None, rows=None):
     ctx = lib.Context(device=0, lowpass=lowpass, y_down=y_down, zclip_mode=zclip_mode)
     ctx.upload(scene)
     fb = np.zeros((H, W), np.uint32) if fb0 is None else fb0.copy()
@@ -253,7 +253,7 @@ def test_near_cut_stripes_and_empty_regions(lib, orc):
         ctx.close()
 
 
-@pytest.mark.parametrize("y_down,zclip", [(0, 0), (1, 1), (0, 2)])
+@pytest.mark.parametrize("y_down,zclip", [(1, 0), (0, 0), (1, 1), (0, 2)])
 def test_euc_switches(lib, orc, y_down, zclip):
     W, H = 400, 300
     scene = _scene(5_000, 0x5EED0031, -3.5)
