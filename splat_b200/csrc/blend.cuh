@@ -199,8 +199,30 @@ SPLAT_DEVINL void mbar_arrive(uint64_t *bar) {
 // a suspend-time hint (measured on B200: the suspended warp is woken by unrelated barrier
 // traffic and re-polls ~10^9 times per frame, 21% of all issued instructions in r1d).
 // MODE 2: test_wait, then nanosleep with a short back-off -- a sleeping warp issues nothing.
+SPLAT_DEVINL bool mbar_test(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0u;
+}
+constexpr uint32_t WD_POLLS = 1u << 22;
+// wd: 8 words of mapped pinned host memory (splat_ctx::h_wd): [0] tripped, [1] block, [2] thread,
+// [3] tag = role << 28 | slot << 20 | chunk (low 20 bits), [4] parity waited for
+__device__ __noinline__ void watchdog_trip(uint32_t *wd, uint32_t tag, uint32_t parity) {
+  if (wd && atomicCAS(&wd[0], 0u, 1u) == 0u) {
+    wd[1] = blockIdx.x; wd[2] = threadIdx.x; wd[3] = tag; wd[4] = parity;
+    __threadfence_system();
+  }
+  __trap();
+}
 template <int MODE>
-SPLAT_DEVINL void mbar_wait(uint64_t *bar, uint32_t parity, const uint32_t *gword = nullptr) {
+SPLAT_DEVINL void mbar_wait(uint64_t *bar, uint32_t parity, const uint32_t *gword = nullptr, uint32_t *wd = nullptr,
+                            uint32_t tag = 0) {
   if (MODE == 0) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -240,17 +262,15 @@ SPLAT_DEVINL void mbar_wait(uint64_t *bar, uint32_t parity, const uint32_t *gwor
         "r"(parity), "l"(gword)
         : "memory");
   } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "WAIT_%=:\n\t"
-        "nanosleep.u32 %2;\n\t"
-        "mbarrier.test_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t"
-        "@!p bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-        "r"(parity), "n"(MODE == 2 ? SPLAT_SLEEP_NS : SPLAT_SLEEP_NS_CONSUMER)
-        : "memory");
+    // test_wait, then nanosleep with a short back-off -- a sleeping warp issues nothing.  The poll
+    // count doubles as a watchdog: no legitimate wait in this kernel lasts longer than a few hundred
+    // microseconds, so after WD_POLLS polls (>= 0.1 s) the warp records who was waiting for what in
+    // host-visible memory and traps; the host then reports SPLAT_ERR_CUDA instead of hanging.
+    uint32_t polls = 0;
+    while (!mbar_test(bar, parity)) {
+      __nanosleep(MODE == 2 ? SPLAT_SLEEP_NS : SPLAT_SLEEP_NS_CONSUMER);
+      if (++polls > WD_POLLS) watchdog_trip(wd, tag, parity);
+    }
   }
 }
 #ifndef SPLAT_WAIT_CONSUMER
@@ -380,7 +400,8 @@ __global__ void __launch_bounds__(BL_THREADS, 3)
 blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
              const uint32_t *__restrict__ n_units, const uint32_t *__restrict__ inst_vals, const Rec *__restrict__ recs,
              uint32_t *__restrict__ fb_rows, const __grid_constant__ FrameParams P,
-             const uint32_t *__restrict__ far_cnt, FrameStatus *__restrict__ status, uint32_t *__restrict__ tile_failed) {
+             const uint32_t *__restrict__ far_cnt, FrameStatus *__restrict__ status, uint32_t *__restrict__ tile_failed,
+             uint32_t *__restrict__ wd) {
   extern __shared__ __align__(16) unsigned char blend_smem_raw[];
   BlendSmem &S = *reinterpret_cast<BlendSmem *>(blend_smem_raw);
 
@@ -549,7 +570,8 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
         const uint32_t chunk_end = min(s_end, (chunk + 1) * BL_CH);
         const uint32_t slot = (gl << d_log) + (chunk & d_mask);
         if (s % BL_CH == 0) {
-          mbar_wait<SPLAT_WAIT_PRODUCER>(&S.empty[slot], ((chunk >> d_log) & 1u) ^ 1u, n_units);
+          mbar_wait<SPLAT_WAIT_PRODUCER>(&S.empty[slot], ((chunk >> d_log) & 1u) ^ 1u, n_units, wd,
+                                         (1u << 28) | (slot << 20) | (chunk & 0xFFFFFu));
           nout = 0;
         }
         RingEntry *slotp = &S.ring[slot][nout];
@@ -622,7 +644,8 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
       if (evaluates && (chunk & ev_mask) == p) {
         const uint32_t slot = (gl << d_log) + (chunk & d_mask);
         if (rem == 0) {
-          mbar_wait<SPLAT_WAIT_PRODUCER>(&S.empty[slot], ((chunk >> d_log) & 1u) ^ 1u, n_units);
+          mbar_wait<SPLAT_WAIT_PRODUCER>(&S.empty[slot], ((chunk >> d_log) & 1u) ^ 1u, n_units, wd,
+                                         (2u << 28) | (slot << 20) | (chunk & 0xFFFFFu));
           nout = 0;
         }
         __syncwarp();
@@ -693,7 +716,8 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
 
     for (uint32_t chunk = 0;; ++chunk) {
       const uint32_t slot = (gl << d_log) + (chunk & d_mask);
-      mbar_wait<SPLAT_WAIT_CONSUMER>(&S.full[slot], (chunk >> d_log) & 1u, n_units);
+      mbar_wait<SPLAT_WAIT_CONSUMER>(&S.full[slot], (chunk >> d_log) & 1u, n_units, wd,
+                                     (3u << 28) | (slot << 20) | (chunk & 0xFFFFFu));
       const uint32_t h = S.hdr[slot];
       const uint32_t n = h & 0xFFu;
       const RingEntry *ep = &S.ring[slot][0];

@@ -14,8 +14,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <new>
 #include <string>
+#include <thread>
 
 #include "../../include/splat.h"
 #include "bin.cuh"
@@ -66,6 +68,9 @@ struct splat_ctx {
   uint64_t last_cut_instances = 0; // (tile, Gaussian) pairs it did not bin
   uint32_t *n_units = nullptr;
   FrameStatus *d_status = nullptr, *h_status = nullptr;
+  uint32_t *h_wd = nullptr, *d_wd = nullptr;   // blend watchdog record (mapped pinned host memory, blend.cuh)
+  bool debug_sync = false;                     // SPLAT_DEBUG_SYNC=1: bounded wait after every launch, names the kernel that hangs
+  double wait_limit_s = 30.0;                  // SPLAT_WAIT_LIMIT_S: bound of every host wait on the device
   uint32_t *d_fb = nullptr; size_t fb_cap = 0;
 
   // last frame
@@ -91,6 +96,42 @@ int fail(splat_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess) 
     if (e__ != cudaSuccess) return fail(c, e__ == cudaErrorMemoryAllocation ? SPLAT_ERR_NOMEM : SPLAT_ERR_CUDA, #expr, e__); \
   } while (0)
 
+// Bounded host wait: polls instead of blocking, so that a kernel that never finishes becomes an
+// error code with a message (which wait, and the blend watchdog's record if it tripped), not a hang.
+int wait_done(splat_ctx *c, cudaEvent_t ev, cudaStream_t s, const char *what) {
+  const auto t0 = std::chrono::steady_clock::now();
+  for (unsigned spins = 0;; ++spins) {
+    const cudaError_t e = ev ? cudaEventQuery(ev) : cudaStreamQuery(s);
+    if (e == cudaSuccess) return SPLAT_OK;
+    if (e != cudaErrorNotReady) {
+      int rc = fail(c, SPLAT_ERR_CUDA, what, e);
+      if (c->h_wd && c->h_wd[0]) {
+        char buf[160];
+        std::snprintf(buf, sizeof buf, " [blend watchdog: block %u thread %u role %u slot %u chunk %u parity %u]", c->h_wd[1],
+                      c->h_wd[2], c->h_wd[3] >> 28, (c->h_wd[3] >> 20) & 0xFFu, c->h_wd[3] & 0xFFFFFu, c->h_wd[4]);
+        c->err += buf;
+      }
+      return rc;
+    }
+    if (spins > 2000) {
+      const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      if (dt > c->wait_limit_s) {
+        c->err = std::string("timeout waiting for the device: ") + what;
+        return SPLAT_ERR_CUDA;
+      }
+      if (dt > 0.002) std::this_thread::sleep_for(std::chrono::microseconds(50));
+    }
+  }
+}
+#define LAUNCHED(name)                                                        \
+  do {                                                                        \
+    c->launches += 1;                                                         \
+    if (c->debug_sync) {                                                      \
+      int rc__ = wait_done(c, nullptr, s, name);                              \
+      if (rc__) return rc__;                                                  \
+    }                                                                         \
+  } while (0)
+
 template <typename T>
 cudaError_t dev_alloc(T **p, size_t count) {
   return cudaMalloc(reinterpret_cast<void **>(p), std::max<size_t>(count, 1) * sizeof(T));
@@ -104,7 +145,7 @@ void dev_free(T *&p) {
 inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
 
 // stable LSD radix sort of (key, value) pairs on bits [0, bits); returns the buffer index
-// (0/1) that holds the result.  `n` sizes the grid; if n_ptr is set the kernels sort only the
+// (0/1) that holds the result, or a negative error code (SPLAT_DEBUG_SYNC runs).  `n` sizes the grid; if n_ptr is set the kernels sort only the
 // first *n_ptr pairs (a device-side count <= n).
 int radix_sort(splat_ctx *c, cudaStream_t s, uint32_t *keys[2], uint32_t *vals[2], uint32_t n, int bits,
                int cur = 0, const uint32_t *n_ptr = nullptr) {
@@ -120,7 +161,8 @@ int radix_sort(splat_ctx *c, cudaStream_t s, uint32_t *keys[2], uint32_t *vals[2
     else
       rs_scatter_kernel<0><<<nblk, RS_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1],
                                                        n_ptr, n, shift, nbits, c->hist, c->tot, nblk);
-    c->launches += 3;
+    c->launches += 2;
+    LAUNCHED("radix sort pass (hist, rowscan, scatter)");
     cur ^= 1;
   }
   return cur;
@@ -260,24 +302,26 @@ int render_back(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cudaS
     far_cover_kernel<<<148, FC_THREADS, cells * sizeof(int), s>>>(c->vals[cur], c->rects, n_sorted, n, rank_cut,
                                                                   P.tiles_x, P.tiles_y, c->far_diff);
     far_prefix_kernel<<<1, 1024, cells * sizeof(int), s>>>(c->far_diff, P.tiles_x, P.tiles_y, c->far_cnt, c->d_status);
-    c->launches += 2;
+    c->launches += 1;
+    LAUNCHED("far_cover / far_prefix");
     far = c->far_cnt;
   }
   tile_count_kernel<<<cdiv(n, 256), 256, 0, s>>>(c->keys[cur], c->vals[cur], c->tcnt, c->cnt, n, n_sorted, rank_cut, c->d_status,
                                                   only_box ? c->rects : nullptr, box);
-  c->launches += 1;
+  LAUNCHED("tile_count_kernel");
   // exclusive scan cnt -> offs, grand total -> status.n_instances
   {
     const uint32_t np = std::max(1u, cdiv(n, SC_BLOCK));
     scan_reduce_kernel<<<np, SC_THREADS, 0, s>>>(c->cnt, c->partial, n);
     scan_partials_kernel<<<1, 1024, 0, s>>>(c->partial, np, &c->d_status->n_instances);
     scan_apply_kernel<<<np, SC_THREADS, 0, s>>>(c->cnt, c->offs, c->partial, n);
-    c->launches += 3;
+    c->launches += 2;
+    LAUNCHED("scan (tile counts)");
   }
   CU(cudaEventRecord(c->ev[EV_COUNT], s));
   CU(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(FrameStatus), cudaMemcpyDeviceToHost, s));
   CU(cudaEventRecord(c->status_ev, s));
-  CU(cudaEventSynchronize(c->status_ev));   // host round trip: the instance count sizes the next launches
+  { int rcw = wait_done(c, c->status_ev, s, "tile count (first half of the frame)"); if (rcw) return rcw; }   // host round trip: the instance count sizes the next launches
   const uint64_t I = c->h_status->n_instances;
   c->last_instances = I;
   c->last_visible = c->h_status->n_visible;
@@ -291,33 +335,34 @@ int render_back(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cudaS
   if (I > 0) {
     emit_instances_kernel<<<cdiv(n, 256), 256, 0, s>>>(c->vals[cur], c->rects, c->cnt, c->offs,
                                                         c->ikeys[0], c->ivals[0], n, P.tiles_x, box);
-    c->launches += 1;
+    LAUNCHED("emit_instances_kernel");
   }
   CU(cudaEventRecord(c->ev[EV_EMIT], s));
   if (I > 0) icur = radix_sort(c, s, c->ikeys, c->ivals, (uint32_t)I, ilog2_ceil(T));
+  if (icur < 0) return icur;
   CU(cudaEventRecord(c->ev[EV_TSORT], s));
   CU(cudaMemsetAsync(c->ranges, 0, (size_t)T * sizeof(uint2), s));
   if (I > 0) {
     tile_ranges_kernel<<<cdiv(I, 1024), 256, 0, s>>>(c->ikeys[icur], (uint32_t)I, c->ranges);
-    c->launches += 1;
+    LAUNCHED("tile_ranges_kernel");
   }
   if (I > 0 || far) {
     unit_order_kernel<<<1, 1024, 0, s>>>(c->ranges, T, c->units, c->n_units, &c->d_status->n_instances, far, c->d_status, P.tiles_x,
                                          c->tile_failed, only_failed ? 1 : 0);   // heaviest first
-    c->launches += 1;
+    LAUNCHED("unit_order_kernel");
   }
   CU(cudaEventRecord(c->ev[EV_RANGES], s));
   if (wait_ev) CU(cudaStreamWaitEvent(s, wait_ev, 0));
   if (I > 0) {
     blend_kernel<<<4 * T, BL_THREADS, BL_SMEM_BYTES, s>>>(c->ranges, c->units, c->n_units, c->ivals[icur], c->recs, fb_rows_dev, P,
-                                                          far, c->d_status, c->tile_failed);
-    c->launches += 1;
+                                                          far, c->d_status, c->tile_failed, c->d_wd);
+    LAUNCHED("blend_kernel");
   }
   CU(cudaEventRecord(c->ev[EV_BLEND], s));
   if (rank_cut) {
     CU(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(FrameStatus), cudaMemcpyDeviceToHost, s));
     CU(cudaEventRecord(c->status_ev, s));
-    CU(cudaEventSynchronize(c->status_ev));   // did every pixel converge on the near lists?
+    { int rcw = wait_done(c, c->status_ev, s, "near-cut pass (bin, sort, blend)"); if (rcw) return rcw; }   // did every pixel converge on the near lists?
   }
   return SPLAT_OK;
 }
@@ -330,7 +375,7 @@ int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cuda
   CU(cudaEventRecord(c->ev[EV_START], s));
   CU(cudaMemsetAsync(c->d_status, 0, sizeof(FrameStatus), s));
   project_kernel<<<cdiv(n, 256), 256, 0, s>>>(c->scene, P, c->recs, c->keys[0], c->vals[0], c->rects, c->tcnt, c->block_kept);
-  c->launches += 1;
+  LAUNCHED("project_kernel");
   CU(cudaEventRecord(c->ev[EV_PROJECT], s));
   int cur = 0;
   const uint32_t *n_sorted = nullptr;
@@ -341,11 +386,13 @@ int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cuda
     scan_partials_kernel<<<1, 1024, 0, s>>>(c->partial, np, &c->d_status->n_sort);
     scan_apply_kernel<<<np, SC_THREADS, 0, s>>>(c->block_kept, c->block_kept, c->partial, nb);
     compact_pairs_kernel<<<nb, 256, 0, s>>>(c->keys[0], c->vals[0], c->keys[1], c->vals[1], c->block_kept, n);
-    c->launches += 4;
+    c->launches += 3;
+    LAUNCHED("stripe compaction");
     cur = 1;
     n_sorted = reinterpret_cast<const uint32_t *>(&c->d_status->n_sort);   // low word (n < 2^31)
   }
   cur = radix_sort(c, s, c->keys, c->vals, n, 32, cur, n_sorted);
+  if (cur < 0) return cur;
   c->order_buf = cur;
   CU(cudaEventRecord(c->ev[EV_DSORT], s));
 
@@ -444,6 +491,11 @@ int splat_create(splat_ctx **out, const splat_config *cfg) {
   if (dev_alloc(&c->n_units, 1) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
   if (dev_alloc(&c->tot, 256) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
   if (cudaMallocHost(reinterpret_cast<void **>(&c->h_status), sizeof(FrameStatus)) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
+  if (cudaHostAlloc(reinterpret_cast<void **>(&c->h_wd), 8 * sizeof(uint32_t), cudaHostAllocMapped) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
+  std::memset(c->h_wd, 0, 8 * sizeof(uint32_t));
+  if (cudaHostGetDevicePointer(reinterpret_cast<void **>(&c->d_wd), c->h_wd, 0) != cudaSuccess) return bail(SPLAT_ERR_CUDA);
+  if (const char *e = std::getenv("SPLAT_DEBUG_SYNC")) c->debug_sync = e[0] == '1';
+  if (const char *e = std::getenv("SPLAT_WAIT_LIMIT_S")) { const double v = std::atof(e); if (v > 0.0) c->wait_limit_s = v; }
   *out = c;
   return SPLAT_OK;
 }
@@ -456,6 +508,7 @@ void splat_destroy(splat_ctx *c) {
   dev_free(c->hist); dev_free(c->tot); dev_free(c->partial); dev_free(c->ranges); dev_free(c->units); dev_free(c->far_cnt); dev_free(c->far_diff); dev_free(c->tile_failed); dev_free(c->n_units); dev_free(c->d_status); dev_free(c->d_fb);
   for (int k = 0; k < 2; ++k) { dev_free(c->ikeys[k]); dev_free(c->ivals[k]); }
   if (c->h_status) cudaFreeHost(c->h_status);
+  if (c->h_wd) cudaFreeHost(c->h_wd);
   for (int i = 0; i < EV_COUNT_; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->status_ev) cudaEventDestroy(c->status_ev);
   if (c->h2d_done) cudaEventDestroy(c->h2d_done);
@@ -549,7 +602,7 @@ int splat_render_rows(splat_ctx *c, const splat_camera *cam, uint32_t *fb_rows, 
   CU(cudaEventRecord(c->ev[EV_D2H0], c->stream));
   CU(cudaMemcpyAsync(fb_rows, c->d_fb, px * 4, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaEventRecord(c->ev[EV_D2H1], c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  { int rcw = wait_done(c, nullptr, c->stream, "frame (kernels + framebuffer download)"); if (rcw) return rcw; }
   c->host_copy = true;
   return SPLAT_OK;
 }
@@ -586,7 +639,7 @@ int splat_render_cleared(splat_ctx *c, const splat_camera *cam, uint32_t *fb_out
   CU(cudaEventRecord(c->ev[EV_D2H0], c->stream));
   CU(cudaMemcpyAsync(fb_out, c->d_fb, px * 4, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaEventRecord(c->ev[EV_D2H1], c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  { int rcw = wait_done(c, nullptr, c->stream, "frame (kernels + framebuffer download)"); if (rcw) return rcw; }
   c->host_copy = true;
   return SPLAT_OK;
 }
@@ -682,10 +735,13 @@ int splat_debug_sort_pairs(splat_ctx *c, uint32_t *keys, uint32_t *vals, uint64_
     cudaMemcpy(k[0], keys, n * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(v[0], vals, n * 4, cudaMemcpyHostToDevice);
     const int cur = radix_sort(c, c->stream, k, v, (uint32_t)n, bits);
-    cudaStreamSynchronize(c->stream);
-    cudaMemcpy(keys, k[cur], n * 4, cudaMemcpyDeviceToHost);
-    cudaMemcpy(vals, v[cur], n * 4, cudaMemcpyDeviceToHost);
-    if (cudaGetLastError() != cudaSuccess) rc = fail(c, SPLAT_ERR_CUDA, "debug sort");
+    if (cur < 0) rc = cur;
+    else {
+      cudaStreamSynchronize(c->stream);
+      cudaMemcpy(keys, k[cur], n * 4, cudaMemcpyDeviceToHost);
+      cudaMemcpy(vals, v[cur], n * 4, cudaMemcpyDeviceToHost);
+      if (cudaGetLastError() != cudaSuccess) rc = fail(c, SPLAT_ERR_CUDA, "debug sort");
+    }
   }
   for (int i = 0; i < 2; ++i) { dev_free(k[i]); dev_free(v[i]); }
   c->n = saved_n;

@@ -117,24 +117,59 @@ def naive_gaussians() -> List[Gaussian]:
 _GOLDEN = np.uint64(0x9E3779B97F4A7C15)
 
 
-def _splitmix64(seed: int, stream: int, n: int) -> np.ndarray:
-    """n 64-bit outputs of splitmix64 started at seed + stream*2^40 (counter based)."""
+def _splitmix64(seed: int, stream: int, a: int, b: int) -> np.ndarray:
+    """outputs a+1 .. b of splitmix64 started at seed + stream*2^40 (counter based)."""
     with np.errstate(over="ignore"):
         base = np.uint64(seed) + np.uint64(stream) * np.uint64(1 << 40)
-        z = base + (np.arange(1, n + 1, dtype=np.uint64)) * _GOLDEN
+        z = base + (np.arange(a + 1, b + 1, dtype=np.uint64)) * _GOLDEN
         z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
         z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
         return z ^ (z >> np.uint64(31))
 
 
-def _uniform(seed, stream, n):
-    return ((_splitmix64(seed, stream, n) >> np.uint64(11)).astype(np.float64) + 0.5) * (1.0 / (1 << 53))
+def _uniform(seed, stream, a, b):
+    return ((_splitmix64(seed, stream, a, b) >> np.uint64(11)).astype(np.float64) + 0.5) * (1.0 / (1 << 53))
 
 
-def _normal(seed, stream, n):
-    u1 = _uniform(seed, 2 * stream, n)
-    u2 = _uniform(seed, 2 * stream + 1, n)
+def _normal(seed, stream, a, b):
+    u1 = _uniform(seed, 2 * stream, a, b)
+    u2 = _uniform(seed, 2 * stream + 1, a, b)
     return np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+
+
+def _synthetic_range(seed: int, log_scale_mean: float, a: int, b: int, out) -> None:
+    """Gaussians [a, b) of synthetic_scene, written into the preallocated f32 arrays `out`.  The
+    generator is counter based, so any split into ranges gives the same bytes."""
+    n = b - a
+    s = 0
+    def nrm(k=1):
+        nonlocal s
+        cols = []
+        for _ in range(k):
+            cols.append(_normal(seed, s, a, b)); s += 1
+        return np.stack(cols, axis=1) if k > 1 else cols[0]
+    def uni(k=1):
+        nonlocal s
+        cols = []
+        for _ in range(k):
+            cols.append(_uniform(seed, 1000 + s, a, b)); s += 1
+        return np.stack(cols, axis=1) if k > 1 else cols[0]
+
+    pos, scales, opac, rot, sh = out
+    is_obj = uni() < 0.7
+    obj = nrm(3) * 0.6
+    bg = uni(3) * 8.0 - 4.0
+    pos[a:b, :3] = np.where(is_obj[:, None], obj, bg)
+    pos[a:b, 3] = 1.0
+    base = nrm() * 0.8 + log_scale_mean
+    scales[a:b] = np.exp(base[:, None] + nrm(3) * 0.5)
+    q = nrm(4)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    rot[a:b] = q
+    opac[a:b] = 1.0 / (1.0 + np.exp(-(nrm() * 2.0 + 0.5)))
+    sh[a:b, 0:3] = (nrm(3) * 0.35 + 0.5 - 0.5) / 0.28209479177387814
+    sh[a:b, 3:27] = nrm(24) * 0.15
+    assert n >= 0
 
 
 def synthetic_scene(n: int, seed: int = 0x5EED0000, log_scale_mean: float = -4.0) -> GaussianList:
@@ -143,36 +178,23 @@ def synthetic_scene(n: int, seed: int = 0x5EED0000, log_scale_mean: float = -4.0
     U([-4,4]^3); log-scale N(log_scale_mean, 0.8^2) per Gaussian plus N(0, 0.5^2) per axis;
     random unit rotations; opacity sigmoid(N(0.5, 2^2)); DC colour N(0.5, 0.35^2) (a few
     percent outside [0,1] to exercise the unclamped-colour / saturating-cast path); 24
-    higher-order SH coefficients N(0, 0.15^2); degree-3 coefficients zero."""
-    s = 0
-    def nrm(k=1):
-        nonlocal s
-        cols = []
-        for _ in range(k):
-            cols.append(_normal(seed, s, n)); s += 1
-        return np.stack(cols, axis=1) if k > 1 else cols[0]
-    def uni(k=1):
-        nonlocal s
-        cols = []
-        for _ in range(k):
-            cols.append(_uniform(seed, 1000 + s, n)); s += 1
-        return np.stack(cols, axis=1) if k > 1 else cols[0]
+    higher-order SH coefficients N(0, 0.15^2); degree-3 coefficients zero.  Large scenes are
+    generated in ranges on a thread pool (numpy releases the GIL); the bytes do not depend on
+    the split."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
 
-    is_obj = uni() < 0.7
-    obj = nrm(3) * 0.6
-    bg = uni(3) * 8.0 - 4.0
-    xyz = np.where(is_obj[:, None], obj, bg)
-    base = nrm() * 0.8 + log_scale_mean
-    scales = np.exp(base[:, None] + nrm(3) * 0.5)
-    q = nrm(4)
-    q /= np.linalg.norm(q, axis=1, keepdims=True)
-    opac = 1.0 / (1.0 + np.exp(-(nrm() * 2.0 + 0.5)))
-    sh = np.zeros((n, 48))
-    sh[:, 0:3] = (nrm(3) * 0.35 + 0.5 - 0.5) / 0.28209479177387814
-    sh[:, 3:27] = nrm(24) * 0.15
-    pos = np.ones((n, 4))
-    pos[:, :3] = xyz
-    return GaussianList(pos, scales, opac, q, sh)
+    out = (np.zeros((n, 4), f32), np.zeros((n, 3), f32), np.zeros(n, f32), np.zeros((n, 4), f32), np.zeros((n, 48), f32))
+    step = 1 << 17
+    ranges = [(a, min(a + step, n)) for a in range(0, n, step)]
+    workers = min(len(ranges), os.cpu_count() or 1)
+    if workers <= 1:
+        for a, b in ranges:
+            _synthetic_range(seed, log_scale_mean, a, b, out)
+    else:
+        with ThreadPoolExecutor(workers) as ex:
+            list(ex.map(lambda r: _synthetic_range(seed, log_scale_mean, r[0], r[1], out), ranges))
+    return GaussianList(*out)
 
 
 # --------------------------------------------------------------------------- PLY (f-1)

@@ -141,6 +141,50 @@ def test_framebuffer_bit_exact(lib, orc, case):
     assert np.array_equal(fb, ref), f"{np.count_nonzero(fb != ref)} of {W*H} pixels differ"
 
 
+def test_config2_plush_sized_complete_frame(lib, orc):
+    """BASELINE config 2 at full size: 281,498 Gaussians (the plush scene's count, notebook cell 5),
+    1280x720, the demo camera of 02_ply_demo.rs:22 -- every pixel against the oracle."""
+    W, H = 1280, 720
+    scene = _scene(281_498, 0x5EED0002)
+    cam = _camera(W, H, DEMO_CAM)
+    fb, ref, t, st = _render_both(lib, orc, scene, cam, W, H)
+    assert t["n_visible"] == st.n_visible and st.pairs_in_rect > 10_000_000
+    assert np.array_equal(fb, ref), f"{np.count_nonzero(fb != ref)} of {W*H} pixels differ"
+
+
+FULL_SIZE = [
+    # name, n, seed, W, H, camera, tile-row stripes compared with the oracle
+    ("config3_bicycle_sized_1080p", 6_100_000, 0x5EED0003, 1920, 1080, (0.0, 0.0, 5.0), (3, 20, 33, 34, 47, 66)),
+    ("config4_garden_sized_4k", 5_800_000, 0x5EED0004, 3840, 2160, DEMO_CAM, (10, 52, 67, 68, 101, 130)),
+]
+
+
+@pytest.mark.parametrize("case", FULL_SIZE, ids=[c[0] for c in FULL_SIZE])
+def test_full_size_configs_sampled_stripes(lib, orc, case):
+    """BASELINE configs 3 and 4 at full size.  The GPU renders the whole frame; the oracle projects
+    and sorts the whole scene and rasterises six 16-row tile stripes of it (the centre rows hold the
+    deepest lists); those rows must be bit-identical, all four bytes of every pixel."""
+    name, n, seed, W, H, pos, stripes = case
+    scene = _scene(n, seed)
+    cam = _camera(W, H, pos, yaw=0.3)
+    ctx = lib.Context(device=0)
+    ctx.upload(scene)
+    fb = np.zeros((H, W), np.uint32)
+    ctx.render(lib.camera_struct(cam), fb)
+    t = ctx.timings()
+    ctx.close()
+    cfg = orc.make_config()
+    sp = orc.project(scene, orc.camera_from(cam), cfg, W, H)
+    order = orc.sort_visible(sp)
+    assert t["n_visible"] == len(order)
+    rows = np.concatenate([np.arange(16 * r, min(16 * r + 16, H)) for r in stripes])
+    ref = np.zeros((H, W), np.uint32)
+    st = orc.rasterize_rows(sp, order, cfg, ref, rows)
+    assert st.pairs_in_rect > 50_000_000 and np.count_nonzero(ref[rows]) > len(rows) * W // 2
+    bad = int(np.count_nonzero(fb[rows] != ref[rows]))
+    assert bad == 0, f"{bad} of {len(rows) * W} pixels differ"
+
+
 def test_blends_onto_existing_contents(lib, orc):
     """render_to_buffer blends onto whatever the buffer holds (pipelines.rs:147-168 decode the
     old pixel); untouched pixels keep their value including the alpha byte."""
