@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SPLAT_ABI_VERSION 1u
+#define SPLAT_ABI_VERSION 2u
 
 typedef struct splat_ctx splat_ctx;
 
@@ -37,13 +37,23 @@ enum {
   SPLAT_ERR_CUDA = -2,        /* a CUDA runtime call failed; see splat_last_error               */
   SPLAT_ERR_NOMEM = -3,       /* host or device allocation failed                               */
   SPLAT_ERR_UNSUPPORTED = -4, /* e.g. camera.w/h differ from the target size, tile != 16        */
-  SPLAT_ERR_STATE = -5        /* render before upload                                           */
+  SPLAT_ERR_STATE = -5,       /* render before upload                                           */
+  SPLAT_ERR_RETRY = -6        /* the previous splat_render_device frame was skipped on the device (see there);
+                               * the buffers have been grown: render that frame again                */
 };
 
 /* blend_mode values.  Only SPLAT_BLEND_REFERENCE reproduces the reference's pixels
- * (pipelines.rs:147-168: u8 truncation after every Gaussian, far -> near). */
+ * (pipelines.rs:147-168: u8 truncation after every Gaussian, far -> near).
+ * SPLAT_BLEND_FLOAT is the standard un-quantised formulation of the same image: per pixel, nearest
+ * first, C += T*alpha*colour, T *= 1-alpha with the reference's fragment() (pipelines.rs:127-145)
+ * unchanged, stopped when T < 2^-16, then ONE quantisation: byte = (C + T*old/255)*255 truncated,
+ * alpha byte = (1-T)*255; pixels no fragment contributes to are left untouched.  It differs from
+ * the reference by that blend's own per-layer truncation bias (6-9e-3 RMSE) and is
+ * checked against a float CPU restatement (<= 1e-4 RMSE) that is itself pinned to the reference's
+ * Python prototype (notebook cell 3). */
 enum {
-  SPLAT_BLEND_REFERENCE = 0
+  SPLAT_BLEND_REFERENCE = 0,
+  SPLAT_BLEND_FLOAT = 1
 };
 
 /* Behaviour switches.  lowpass selects which reference pipeline is reproduced; the three
@@ -64,6 +74,10 @@ typedef struct {
                             * nearest k/1024 of the Gaussians and redo the tiles that do not converge with all
                             * of them (results identical either way): 0 = off, -1 = automatic (starts at 1/8,
                             * doubles after a whole-frame fall-back), 1..1024 = fixed fraction */
+  int32_t  sync_frames;    /* 1: read the tile-instance count on the host in the middle of every frame (exact
+                            * launch sizes, one round trip per frame).  0 (default): only the first frame of a
+                            * target geometry does; later frames are enqueued without any host wait            */
+  int32_t  reserved;       /* 0 */
 } splat_config;
 
 /* What the kernels need from `Camera` (camera.rs:4-19): the two matrices exactly as nalgebra
@@ -98,11 +112,15 @@ typedef struct {
                              * frames_retried also counts the renders that then needed the complete pass */
   uint64_t near_cut_failed; /* pixel groups / tiles that did not converge in that pass (0 = it was enough) */
   uint64_t near_cut_instances; /* (tile, Gaussian) pairs that pass did not have to bin and sort */
+  uint64_t frames_skipped;  /* since the context was created: frames whose tile instances did not fit the buffers
+                             * on the no-round-trip path (host-buffer calls repeat them themselves)            */
 } splat_timings;
 
 uint32_t    splat_abi_version(void);
 void        splat_config_default(splat_config *cfg);
 int         splat_create(splat_ctx **out, const splat_config *cfg);
+/* why the last splat_create on this thread failed ("" if it did not): there is no context to ask */
+const char *splat_create_error(void);
 void        splat_destroy(splat_ctx *ctx);
 const char *splat_last_error(const splat_ctx *ctx);
 
@@ -139,12 +157,20 @@ int splat_render_rows(splat_ctx *ctx, const splat_camera *cam, uint32_t *fb_rows
 
 /* Device-buffer variant: fb_rows_dev is a device pointer on cfg.device (e.g. the slice of an
  * NCCL-registered gather buffer); work is enqueued on `stream` (a cudaStream_t, NULL = the
- * context's own stream).  The call blocks once mid-frame to read the tile-instance count
- * (8 bytes) and returns after enqueueing the remaining kernels, without waiting for them. */
+ * context's own stream) and the call returns without waiting for it.
+ * The first frame of a target geometry (W, H, row0, row1) blocks once mid-frame to read the
+ * tile-instance count and size the buffers.  Every later frame is enqueued with NO host wait: its
+ * launches are sized from the previous frame, the kernels read the real count on the device, and
+ * the instance buffers are kept at >= 2x the last count.  Should a frame nevertheless want more
+ * instances than the buffers hold (its count more than doubled in one frame), it blends NOTHING:
+ * its target is left exactly as the caller provided it, and the next call on this context
+ * (render or splat_get_timings) grows the buffers and returns SPLAT_ERR_RETRY once -- render that
+ * frame again.  The host-buffer entry points repeat such a frame themselves. */
 int splat_render_device(splat_ctx *ctx, const splat_camera *cam, void *fb_rows_dev, uint32_t W,
                         uint32_t H, uint32_t row0, uint32_t row1, void *stream);
 
-/* Blocks until the last enqueued render finished, then reports its stage times. */
+/* Blocks until the last enqueued render finished, then reports its stage times (all fields describe
+ * that render; frames_skipped is cumulative). */
 int splat_get_timings(splat_ctx *ctx, splat_timings *out);
 
 /* Tile-list lengths of the last completed render: per_tile[ty * tiles_x + tx] = number of
@@ -175,6 +201,10 @@ int splat_debug_sort_pairs(splat_ctx *ctx, uint32_t *keys, uint32_t *vals, uint6
  * [1] group-entries that changed a pixel, [2] (pixel, Gaussian) pairs with alpha > 0,
  * [3] tile-list entries staged, [4] candidate pairs, [5] pixel-pair lanes with alpha > 0. */
 int splat_debug_blend_stats(splat_ctx *ctx, uint64_t *out8, int reset);
+/* SPLAT_BLEND_FLOAT contexts: splat_render, plus the un-quantised result of every pixel a fragment
+ * contributed to: rgba[4*(y*W+x)] = r, g, b, 1-T (NaN where the pixel was not touched). */
+int splat_debug_render_float(splat_ctx *ctx, const splat_camera *cam, uint32_t *fb_inout, uint32_t W, uint32_t H,
+                             float *rgba);
 
 #ifdef __cplusplus
 }

@@ -14,20 +14,22 @@ LIB_PATH = os.environ.get("SPLAT_B200_LIB") or os.path.join(_HERE, "libsplat_b20
 
 SPLAT_OK = 0
 ERRORS = {-1: "SPLAT_ERR_INVALID", -2: "SPLAT_ERR_CUDA", -3: "SPLAT_ERR_NOMEM",
-          -4: "SPLAT_ERR_UNSUPPORTED", -5: "SPLAT_ERR_STATE"}
+          -4: "SPLAT_ERR_UNSUPPORTED", -5: "SPLAT_ERR_STATE", -6: "SPLAT_ERR_RETRY"}
+SPLAT_BLEND_REFERENCE, SPLAT_BLEND_FLOAT = 0, 1
 
 # every symbol include/splat.h declares (tests/test_abi.py checks the header against this list)
-EXPORTS = ["splat_abi_version", "splat_config_default", "splat_create", "splat_destroy",
+EXPORTS = ["splat_abi_version", "splat_config_default", "splat_create", "splat_create_error", "splat_destroy",
            "splat_last_error", "splat_upload_soa", "splat_upload_aos", "splat_render", "splat_render_cleared",
            "splat_render_rows", "splat_render_device", "splat_get_timings", "splat_get_tile_loads", "splat_pin_host",
            "splat_unpin_host", "splat_debug_project", "splat_debug_read_order",
-           "splat_debug_sort_pairs", "splat_debug_blend_stats"]
+           "splat_debug_sort_pairs", "splat_debug_blend_stats", "splat_debug_render_float"]
 
 
 class SplatConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("lowpass", C.c_float), ("y_down", C.c_int32),
                 ("zclip_mode", C.c_int32), ("sample_offset", C.c_float), ("tile", C.c_uint32),
-                ("max_instances", C.c_uint64), ("blend_mode", C.c_int32), ("near_cut", C.c_int32)]
+                ("max_instances", C.c_uint64), ("blend_mode", C.c_int32), ("near_cut", C.c_int32),
+                ("sync_frames", C.c_int32), ("reserved", C.c_int32)]
 
 
 class SplatCamera(C.Structure):
@@ -41,7 +43,8 @@ class SplatTimings(C.Structure):
                 ("blend_ms", C.c_float), ("total_ms", C.c_float), ("h2d_ms", C.c_float),
                 ("d2h_ms", C.c_float), ("frames_retried", C.c_uint32),
                 ("n_gaussians", C.c_uint64), ("n_visible", C.c_uint64), ("n_instances", C.c_uint64),
-                ("n_tiles", C.c_uint64), ("kernel_launches", C.c_uint64), ("near_cut_rank", C.c_uint64), ("near_cut_failed", C.c_uint64), ("near_cut_instances", C.c_uint64)]
+                ("n_tiles", C.c_uint64), ("kernel_launches", C.c_uint64), ("near_cut_rank", C.c_uint64), ("near_cut_failed", C.c_uint64), ("near_cut_instances", C.c_uint64),
+                ("frames_skipped", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -70,6 +73,7 @@ def load():
     L.splat_config_default.argtypes = [C.POINTER(SplatConfig)]
     L.splat_config_default.restype = None
     L.splat_create.argtypes = [C.POINTER(vp), C.POINTER(SplatConfig)]
+    L.splat_create_error.restype = C.c_char_p
     L.splat_destroy.argtypes = [vp]
     L.splat_destroy.restype = None
     L.splat_last_error.argtypes = [vp]
@@ -88,6 +92,7 @@ def load():
     L.splat_debug_read_order.argtypes = [vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.splat_debug_sort_pairs.argtypes = [vp, vp, vp, C.c_uint64, C.c_int]
     L.splat_debug_blend_stats.argtypes = [vp, vp, C.c_int]
+    L.splat_debug_render_float.argtypes = [vp, C.POINTER(SplatCamera), vp, C.c_uint32, C.c_uint32, vp]
     for name in EXPORTS:
         getattr(L, name)  # AttributeError if the .so does not export it
     _lib = L
@@ -118,18 +123,19 @@ def _fp(a):
 class Context:
     """Owns one splat_ctx (one GPU)."""
 
-    def __init__(self, device=0, lowpass=0.3, y_down=0, zclip_mode=1, sample_offset=0.5, max_instances=0, near_cut=0):
+    def __init__(self, device=0, lowpass=0.3, y_down=0, zclip_mode=1, sample_offset=0.5, max_instances=0, near_cut=0,
+                 blend_mode=SPLAT_BLEND_REFERENCE, sync_frames=0):
         self.L = load()
         cfg = SplatConfig()
         self.L.splat_config_default(C.byref(cfg))
         cfg.device, cfg.lowpass, cfg.y_down = device, lowpass, y_down
         cfg.zclip_mode, cfg.sample_offset, cfg.max_instances = zclip_mode, sample_offset, max_instances
-        cfg.near_cut = near_cut
+        cfg.near_cut, cfg.blend_mode, cfg.sync_frames = near_cut, blend_mode, sync_frames
         self.cfg = cfg
         self.h = C.c_void_p()
         rc = self.L.splat_create(C.byref(self.h), C.byref(cfg))
         if rc:
-            raise SplatError(rc, "splat_create failed")
+            raise SplatError(rc, "splat_create failed: " + self.L.splat_create_error().decode())
         self.n = 0
 
     def _check(self, rc):
@@ -174,6 +180,16 @@ class Context:
     def render_device(self, cam: SplatCamera, dev_ptr: int, W: int, H: int, row0=0, row1=None, stream=0):
         self._check(self.L.splat_render_device(self.h, C.byref(cam), dev_ptr, W, H, row0,
                                                H if row1 is None else row1, stream or None))
+
+    def render_float(self, cam: SplatCamera, fb: np.ndarray) -> np.ndarray:
+        """SPLAT_BLEND_FLOAT contexts: render onto fb in place and return the un-quantised (H, W, 4) f32
+        r, g, b, 1-T of every touched pixel (NaN elsewhere)."""
+        assert fb.dtype == np.uint32 and fb.flags["C_CONTIGUOUS"]
+        H, W = int(cam.h), int(cam.w)
+        assert fb.shape == (H, W)
+        rgba = np.zeros((H, W, 4), np.float32)
+        self._check(self.L.splat_debug_render_float(self.h, C.byref(cam), fb.ctypes.data, W, H, rgba.ctypes.data))
+        return rgba
 
     def timings(self) -> dict:
         t = SplatTimings()

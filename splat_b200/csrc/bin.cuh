@@ -141,8 +141,9 @@ __global__ void __launch_bounds__(256)
 emit_instances_kernel(const uint32_t *__restrict__ order, const uint2 *__restrict__ rects,
                       const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ offs,
                       uint32_t *__restrict__ inst_keys, uint32_t *__restrict__ inst_vals, uint32_t n,
-                      uint32_t tiles_x, TileRect box) {
+                      uint32_t tiles_x, TileRect box, const uint32_t *__restrict__ n_eff) {
   __shared__ uint32_t s_off[257];
+  if (*n_eff == 0u) return;     // nothing to emit, or the pairs do not fit the buffers (frame skipped)
   __shared__ uint32_t s_idx[256];
   __shared__ uint2 s_rect[256];
   const uint32_t tid = threadIdx.x, r0 = blockIdx.x * 256u, r = r0 + tid;
@@ -184,28 +185,32 @@ emit_instances_kernel(const uint32_t *__restrict__ order, const uint2 *__restric
 }
 
 // ranges[t] = [start, end) of tile t in the tile-sorted instance list (zeroed beforehand).
-// Four keys per thread (one 16-byte load) plus the two neighbours across the group boundary.
+// Four keys per thread (one 16-byte load) plus the two neighbours across the group boundary;
+// grid-stride over a device-side count (see sort.cuh).
 __global__ void __launch_bounds__(256)
-tile_ranges_kernel(const uint32_t *__restrict__ sorted_tile_keys, uint32_t n,
+tile_ranges_kernel(const uint32_t *__restrict__ sorted_tile_keys, const uint32_t *__restrict__ n_ptr,
                    uint2 *__restrict__ ranges) {
-  const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
-  if (j >= n) return;
-  uint32_t k[6];   // k[0] = key[j-1], k[1..4] = key[j..j+3], k[5] = key[j+4]
-  if (j + 4u <= n) {
-    const uint4 v = *reinterpret_cast<const uint4 *>(sorted_tile_keys + j);
-    k[1] = v.x; k[2] = v.y; k[3] = v.z; k[4] = v.w;
-  } else {
+  const uint32_t n = *n_ptr;
+  for (unsigned long long j64 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * 4ull; j64 < n;
+       j64 += (unsigned long long)gridDim.x * blockDim.x * 4ull) {
+    const uint32_t j = (uint32_t)j64;
+    uint32_t k[6];   // k[0] = key[j-1], k[1..4] = key[j..j+3], k[5] = key[j+4]
+    if (j + 4u <= n) {
+      const uint4 v = *reinterpret_cast<const uint4 *>(sorted_tile_keys + j);
+      k[1] = v.x; k[2] = v.y; k[3] = v.z; k[4] = v.w;
+    } else {
 #pragma unroll
-    for (uint32_t q = 0; q < 4u; ++q) k[1 + q] = (j + q < n) ? sorted_tile_keys[j + q] : 0xFFFFFFFFu;
-  }
-  k[0] = j ? sorted_tile_keys[j - 1u] : 0xFFFFFFFFu;
-  k[5] = (j + 4u < n) ? sorted_tile_keys[j + 4u] : 0xFFFFFFFFu;
+      for (uint32_t q = 0; q < 4u; ++q) k[1 + q] = (j + q < n) ? sorted_tile_keys[j + q] : 0xFFFFFFFFu;
+    }
+    k[0] = j ? sorted_tile_keys[j - 1u] : 0xFFFFFFFFu;
+    k[5] = (j + 4u < n) ? sorted_tile_keys[j + 4u] : 0xFFFFFFFFu;
 #pragma unroll
-  for (uint32_t q = 0; q < 4u; ++q) {
-    if (j + q >= n) break;
-    const uint32_t t = k[1 + q];
-    if (j + q == 0u || k[q] != t) ranges[t].x = j + q;
-    if (j + q + 1u == n || k[2 + q] != t) ranges[t].y = j + q + 1u;
+    for (uint32_t q = 0; q < 4u; ++q) {
+      if (j + q >= n) break;
+      const uint32_t t = k[1 + q];
+      if (j + q == 0u || k[q] != t) ranges[t].x = j + q;
+      if (j + q + 1u == n || k[2 + q] != t) ranges[t].y = j + q + 1u;
+    }
   }
 }
 

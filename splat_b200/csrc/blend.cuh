@@ -211,18 +211,24 @@ SPLAT_DEVINL bool mbar_test(uint64_t *bar, uint32_t parity) {
   return ok != 0u;
 }
 constexpr uint32_t WD_POLLS = 1u << 22;
-// wd: 8 words of mapped pinned host memory (splat_ctx::h_wd): [0] tripped, [1] block, [2] thread,
-// [3] tag = role << 28 | slot << 20 | chunk (low 20 bits), [4] parity waited for
-__device__ __noinline__ void watchdog_trip(uint32_t *wd, uint32_t tag, uint32_t parity) {
+constexpr int WD_WORDS = 128;
+// wd: WD_WORDS words of mapped pinned host memory (splat_ctx::h_wd): [0] tripped, [1] block,
+// [2] thread, [3] tag = role << 28 | slot << 20 | chunk (low 20 bits), [4] parity waited for,
+// [5] number of dump words, [8..] the CTA's synchronisation state (see WdDump)
+struct WdDump { const uint32_t *words; uint32_t n; };
+__device__ __noinline__ void watchdog_trip(uint32_t *wd, uint32_t tag, uint32_t parity, WdDump dump) {
   if (wd && atomicCAS(&wd[0], 0u, 1u) == 0u) {
     wd[1] = blockIdx.x; wd[2] = threadIdx.x; wd[3] = tag; wd[4] = parity;
+    const uint32_t n = min(dump.n, (uint32_t)WD_WORDS - 8u);
+    wd[5] = n;
+    for (uint32_t i = 0; i < n; ++i) wd[8 + i] = dump.words[i];
     __threadfence_system();
   }
   __trap();
 }
 template <int MODE>
 SPLAT_DEVINL void mbar_wait(uint64_t *bar, uint32_t parity, const uint32_t *gword = nullptr, uint32_t *wd = nullptr,
-                            uint32_t tag = 0) {
+                            uint32_t tag = 0, WdDump dump = WdDump{nullptr, 0u}) {
   if (MODE == 0) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -269,7 +275,7 @@ SPLAT_DEVINL void mbar_wait(uint64_t *bar, uint32_t parity, const uint32_t *gwor
     uint32_t polls = 0;
     while (!mbar_test(bar, parity)) {
       __nanosleep(MODE == 2 ? SPLAT_SLEEP_NS : SPLAT_SLEEP_NS_CONSUMER);
-      if (++polls > WD_POLLS) watchdog_trip(wd, tag, parity);
+      if (++polls > WD_POLLS) watchdog_trip(wd, tag, parity, dump);
     }
   }
 }
@@ -308,7 +314,7 @@ __global__ void __launch_bounds__(1024)
 unit_order_kernel(const uint2 *__restrict__ ranges, uint32_t T, uint2 *__restrict__ units,
                   uint32_t *__restrict__ n_units, const unsigned long long *__restrict__ n_instances,
                   const uint32_t *__restrict__ far_cnt, FrameStatus *__restrict__ status, uint32_t tiles_x,
-                  uint32_t *__restrict__ tile_failed, int only_failed) {
+                  uint32_t *__restrict__ tile_failed, int only_failed, int no_split) {
   // only_failed: the pass after a near-cut pass blends nothing but the tiles that pass marked --
   // every other tile is final, and one that was composited from the framebuffer bytes must not
   // be composited onto its own output again
@@ -321,7 +327,8 @@ unit_order_kernel(const uint2 *__restrict__ ranges, uint32_t T, uint2 *__restric
   const uint32_t t4 = 0xFFFFFFFFu, t2 = 0xFFFFFFFFu;
   (void)I;
 #else
-  const uint32_t t4 = (uint32_t)max(4096ull, I / 800ull), t2 = (uint32_t)max(2048ull, I / 3200ull);
+  // no_split: whole tiles only (the float compositor runs one CTA per tile)
+  const uint32_t t4 = no_split ? 0xFFFFFFFFu : (uint32_t)max(4096ull, I / 800ull), t2 = no_split ? 0xFFFFFFFFu : (uint32_t)max(2048ull, I / 3200ull);
 #endif
   auto bucket = [](uint32_t len) -> uint32_t {
     const int b = (int)(16.0f * __log2f((float)len));   // 0 .. 16*32-1
@@ -364,6 +371,13 @@ unit_order_kernel(const uint2 *__restrict__ ranges, uint32_t T, uint2 *__restric
 __device__ unsigned long long g_blend_stats[8];
 #define STAT_ADD(i, v) atomicAdd(&g_blend_stats[i], (unsigned long long)(v))
 #endif
+#ifdef SPLAT_WD_TRACE
+#define WD_TRACE(code, v) do { if (lane == 0) S.trace[w][0] = ((uint32_t)(code) << 28) | ((uint32_t)(v) & 0x0FFFFFFFu); } while (0)
+#define WD_COUNT(v) do { if (lane == 0) S.trace[w][1] = (uint32_t)(v); } while (0)
+#else
+#define WD_TRACE(code, v) do { } while (0)
+#define WD_COUNT(v) do { } while (0)
+#endif
 struct RingEntry {
   float2 al[32];   // per lane: alpha of pixel (x, y) and of pixel (x, y+4); 0 = no change
   float4 col;      // r, g, b (+ the power threshold, unused by the consumer)
@@ -371,8 +385,11 @@ struct RingEntry {
 struct BlendSmem {
   float4 sa[BL_BATCH], sb[BL_BATCH], sc[BL_BATCH];        // staged records (see Rec)
   RingEntry ring[BL_SLOTS][BL_CH];                        // chunk slots, BL_SLOTS / ngroups per team
+  // ---- the block from here to `trace` is what the watchdog dumps (contiguous on purpose)
   uint64_t full[BL_SLOTS], empty[BL_SLOTS];               // mbarriers
   uint32_t hdr[BL_SLOTS];                                 // entries in the chunk | last << 8
+  uint32_t info[8];                                       // tile, ng | g0 << 8, len, start - range.x, whole | truncated << 1, suffix
+  uint32_t trace[BL_THREADS / 32][2];                     // -DSPLAT_WD_TRACE: last checkpoint of every warp
   uint32_t wcount[BL_GROUPS][BL_PRODUCER_THREADS / 32];   // per staging warp, per group
   uint8_t list[BL_GROUPS][BL_BATCH];                      // compacted entry indices per group
   uint32_t fail[BL_GROUPS];                               // per team: the suffix attempt did not converge
@@ -447,6 +464,12 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
   const bool whole = (len <= BL_SUFFIX_MIN_LEN) || (suffix >= len);
   exact = whole && !truncated;
   start = whole ? range.x : range.y - suffix;
+  if (tid == 0) {
+    S.info[0] = tile; S.info[1] = ng | (g0 << 8); S.info[2] = len; S.info[3] = start - range.x;
+    S.info[4] = (whole ? 1u : 0u) | (truncated ? 2u : 0u); S.info[5] = suffix;
+  }
+  const WdDump wdd{reinterpret_cast<const uint32_t *>(&S.full[0]),
+                   (uint32_t)((sizeof(S.full) + sizeof(S.empty) + sizeof(S.hdr) + sizeof(S.info) + sizeof(S.trace)) / 4)};
   if (tid < BL_SLOTS) {
     mbar_init(&S.full[tid], 1);
     mbar_init(&S.empty[tid], 1);
@@ -483,6 +506,7 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
 
     for (uint32_t base = start; base < range.y; base += BL_BATCH) {
       const uint32_t nb = min((uint32_t)BL_BATCH, range.y - base);
+      WD_TRACE(1, base - start);
       producers_sync();   // previous batch no longer read by any producer
       uint32_t bits = 0;
       if (tid < nb) {
@@ -563,6 +587,8 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
       // chunks of BL_CH consecutive list entries of the team are dealt round-robin to its
       // evaluating producers: chunk c belongs to producer (c & ev_mask)
       const uint32_t s_end = seq + n_mine;
+      WD_TRACE(2, s_end);
+      WD_COUNT(seq | (n_mine << 16));
       uint32_t chunk = seq / BL_CH;
       chunk += (p - chunk) & ev_mask;                      // first chunk >= seq/BL_CH owned by p
       for (; evaluates && chunk * BL_CH < s_end; chunk += ev_mask + 1u) {
@@ -570,8 +596,9 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
         const uint32_t chunk_end = min(s_end, (chunk + 1) * BL_CH);
         const uint32_t slot = (gl << d_log) + (chunk & d_mask);
         if (s % BL_CH == 0) {
+          WD_TRACE(3, chunk);
           mbar_wait<SPLAT_WAIT_PRODUCER>(&S.empty[slot], ((chunk >> d_log) & 1u) ^ 1u, n_units, wd,
-                                         (1u << 28) | (slot << 20) | (chunk & 0xFFFFFu));
+                                         (1u << 28) | (slot << 20) | (chunk & 0xFFFFFu), wdd);
           nout = 0;
         }
         RingEntry *slotp = &S.ring[slot][nout];
@@ -622,6 +649,7 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
             S.hdr[slot] = nout;
             mbar_arrive(&S.full[slot]);
           }
+          WD_TRACE(4, chunk);
         }
       }
       seq = s_end;
@@ -644,8 +672,9 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
       if (evaluates && (chunk & ev_mask) == p) {
         const uint32_t slot = (gl << d_log) + (chunk & d_mask);
         if (rem == 0) {
+          WD_TRACE(5, chunk);
           mbar_wait<SPLAT_WAIT_PRODUCER>(&S.empty[slot], ((chunk >> d_log) & 1u) ^ 1u, n_units, wd,
-                                         (2u << 28) | (slot << 20) | (chunk & 0xFFFFFu));
+                                         (2u << 28) | (slot << 20) | (chunk & 0xFFFFFu), wdd);
           nout = 0;
         }
         __syncwarp();
@@ -654,6 +683,7 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
           mbar_arrive(&S.full[slot]);
         }
       }
+      WD_TRACE(6, seq);
     }
   } else {
     // ============================== CONSUMERS ==============================
@@ -716,8 +746,9 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
 
     for (uint32_t chunk = 0;; ++chunk) {
       const uint32_t slot = (gl << d_log) + (chunk & d_mask);
+      WD_TRACE(7, chunk);
       mbar_wait<SPLAT_WAIT_CONSUMER>(&S.full[slot], (chunk >> d_log) & 1u, n_units, wd,
-                                     (3u << 28) | (slot << 20) | (chunk & 0xFFFFFu));
+                                     (3u << 28) | (slot << 20) | (chunk & 0xFFFFFu), wdd);
       const uint32_t h = S.hdr[slot];
       const uint32_t n = h & 0xFFu;
       const RingEntry *ep = &S.ring[slot][0];

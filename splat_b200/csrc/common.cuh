@@ -44,7 +44,7 @@ struct Rec {
   float4 a, b, c;
 };
 
-// Frame status written by the device, copied to pinned host memory once per frame.
+// Frame status written by the device, copied to pinned host memory at the end of every frame.
 struct FrameStatus {
   unsigned long long n_instances;  // total (tile, Gaussian) pairs wanted
   unsigned int n_visible;
@@ -52,7 +52,13 @@ struct FrameStatus {
   unsigned int fail_ix0, fail_iy0; // bounding box of those tiles: ~min x, ~min y (kept as maxima so that 0 = none)
   unsigned int fail_x1, fail_y1;   //                             max x, max y
   unsigned long long n_cut;        // near-cut frames: (tile, Gaussian) pairs that were not binned
+  // ---- everything above is zeroed at the start of every binning pass
   unsigned long long n_sort;       // stripe renders: (key, index) pairs that enter the depth sort
+  unsigned int n_inst_eff;         // pairs the kernels behind the count process: n_instances, or 0 if they do not fit
+  unsigned int overflow;           // this frame wanted more pairs than the instance buffers hold: nothing was blended
+  // ---- everything above is zeroed at the start of every frame
+  unsigned int skipped;            // frames skipped that way since the context was created (never zeroed)
+  unsigned int pad_;
 };
 
 #define SPLAT_DEVINL __device__ __forceinline__

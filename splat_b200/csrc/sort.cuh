@@ -32,38 +32,50 @@ SPLAT_DEVINL uint32_t rs_count(const uint32_t *n_ptr, uint32_t n_fixed) {
   return n_ptr ? *n_ptr : n_fixed;
 }
 
-// hist[d * nblk + blk] = number of keys of block blk whose digit is d.
+// All three kernels of a pass take the pair count from device memory (n_ptr, or n_fixed if null),
+// so the LAUNCH never depends on a count the host has not seen yet: the frame is enqueued without
+// a host round trip, with a grid sized from the previous frame (splat_api.cu).  One 4096-pair
+// block per CTA; CTAs beyond the real count exit at once, and a count beyond the launched grid is
+// caught on the device before any of these kernels runs (scan_partials_kernel: the frame is
+// skipped and repeated).  A grid-stride loop instead costs the scatter 17 registers (spills).
+//
+// hist[d * nblk + blk] = number of keys of block blk whose digit is d (nblk = ceil(n / 4096)).
 // All 16 keys of a thread are loaded first (four 16-byte loads in flight), then counted with
-// shared-memory atomics.
+// shared-memory atomics.  The digit of the last, partial pass is masked to its `nbits` bits.
 __global__ void __launch_bounds__(RS_THREADS)
 rs_hist_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ n_ptr, uint32_t n_fixed,
-               int shift, uint32_t *__restrict__ hist, uint32_t nblk) {
+               int shift, uint32_t dmask, uint32_t *__restrict__ hist) {
   __shared__ uint32_t h[256];
   const uint32_t n = rs_count(n_ptr, n_fixed);
-  const uint32_t base = blockIdx.x * RS_BLOCK;
-  h[threadIdx.x] = 0;
-  __syncthreads();
-  if (base + RS_BLOCK <= n) {
-    uint4 v[RS_ITEMS / 4];
+  const uint32_t nblk = (n + RS_BLOCK - 1) / RS_BLOCK;
+  const uint32_t blk = blockIdx.x;
+  if (blk >= nblk) return;
+  {
+    const uint32_t base = blk * RS_BLOCK;
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    if (base + RS_BLOCK <= n) {
+      uint4 v[RS_ITEMS / 4];
 #pragma unroll
-    for (int k = 0; k < RS_ITEMS / 4; ++k)
-      v[k] = __ldg(reinterpret_cast<const uint4 *>(keys + base) + k * RS_THREADS + threadIdx.x);
+      for (int k = 0; k < RS_ITEMS / 4; ++k)
+        v[k] = __ldg(reinterpret_cast<const uint4 *>(keys + base) + k * RS_THREADS + threadIdx.x);
 #pragma unroll
-    for (int k = 0; k < RS_ITEMS / 4; ++k) {
-      atomicAdd(&h[(v[k].x >> shift) & 0xFFu], 1u);
-      atomicAdd(&h[(v[k].y >> shift) & 0xFFu], 1u);
-      atomicAdd(&h[(v[k].z >> shift) & 0xFFu], 1u);
-      atomicAdd(&h[(v[k].w >> shift) & 0xFFu], 1u);
+      for (int k = 0; k < RS_ITEMS / 4; ++k) {
+        atomicAdd(&h[(v[k].x >> shift) & dmask], 1u);
+        atomicAdd(&h[(v[k].y >> shift) & dmask], 1u);
+        atomicAdd(&h[(v[k].z >> shift) & dmask], 1u);
+        atomicAdd(&h[(v[k].w >> shift) & dmask], 1u);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < RS_ITEMS; ++k) {
+        const uint32_t idx = base + k * RS_THREADS + threadIdx.x;
+        if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & dmask], 1u);
+      }
     }
-  } else if (base < n) {
-#pragma unroll
-    for (int k = 0; k < RS_ITEMS; ++k) {
-      const uint32_t idx = base + k * RS_THREADS + threadIdx.x;
-      if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & 0xFFu], 1u);
-    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * nblk + blk] = h[threadIdx.x];
   }
-  __syncthreads();
-  hist[threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
 }
 
 // One CTA per digit d: exclusive scan of hist[d][0..nblk) in place (where block blk's keys with
@@ -72,9 +84,12 @@ rs_hist_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ n
 // launches: histogram, this, scatter.
 constexpr int RW_THREADS = 1024;
 __global__ void __launch_bounds__(RW_THREADS)
-rs_rowscan_kernel(uint32_t *__restrict__ hist, uint32_t nblk, uint32_t *__restrict__ tot) {
+rs_rowscan_kernel(uint32_t *__restrict__ hist, const uint32_t *__restrict__ n_ptr, uint32_t n_fixed,
+                  uint32_t *__restrict__ tot) {
   __shared__ uint32_t wsum[RW_THREADS / 32];
   __shared__ uint32_t carry_s;
+  const uint32_t n = rs_count(n_ptr, n_fixed);
+  const uint32_t nblk = (n + RS_BLOCK - 1) / RS_BLOCK;
   uint32_t *row = hist + (size_t)blockIdx.x * nblk;
   const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
   if (threadIdx.x == 0) carry_s = 0;
@@ -102,13 +117,13 @@ rs_rowscan_kernel(uint32_t *__restrict__ hist, uint32_t nblk, uint32_t *__restri
 }
 
 // NB = 8: all eight digit bits (fully unrolled ranking); NB = 0: `nbits` < 8 bits at run time
-// (the last pass of a key whose width is not a multiple of 8).
+// (the last pass of a key whose width is not a multiple of 8; the digit is masked to them).
 template <int NB>
 __global__ void __launch_bounds__(RS_THREADS, RS_MIN_BLOCKS)
 rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                   uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
                   const uint32_t *__restrict__ n_ptr, uint32_t n_fixed, int shift, int nbits,
-                  const uint32_t *__restrict__ hist_scanned, const uint32_t *__restrict__ tot_g, uint32_t nblk) {
+                  const uint32_t *__restrict__ hist_scanned, const uint32_t *__restrict__ tot_g) {
   __shared__ uint32_t cnt[RS_WARPS][256];   // per-warp digit counts, then exclusive warp bases
   __shared__ uint32_t dbase[256];           // block-local start of each digit's run
   __shared__ uint32_t gofs[256];            // global offset of the run minus dbase
@@ -117,11 +132,15 @@ rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
   __shared__ uint32_t wsum[RS_WARPS];
 
   const uint32_t n = rs_count(n_ptr, n_fixed);
-  const uint32_t base = blockIdx.x * RS_BLOCK;
-  if (base >= n) return;
+  const uint32_t nblk = (n + RS_BLOCK - 1) / RS_BLOCK;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
-  const uint32_t nvalid = min((uint32_t)RS_BLOCK, n - base);
   const uint32_t lt_mask = (1u << lane) - 1u;
+  const uint32_t dmask = NB ? 0xFFu : ((1u << nbits) - 1u);
+
+  const uint32_t blk = blockIdx.x;
+  if (blk >= nblk) return;
+  const uint32_t base = blk * RS_BLOCK;
+  const uint32_t nvalid = min((uint32_t)RS_BLOCK, n - base);
 
 #pragma unroll
   for (int q = 0; q < RS_WARPS; ++q) cnt[q][tid] = 0;
@@ -143,7 +162,7 @@ rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
   for (int k = 0; k < RS_ITEMS; ++k) {
     const uint32_t li = w * RS_WARP_SPAN + k * 32 + lane;
     const bool valid = li < nvalid;
-    const uint32_t d = (key[k] >> shift) & 0xFFu;
+    const uint32_t d = (key[k] >> shift) & dmask;
     // (mixing in a few match.any rounds to run on the ADU pipe beside the ballots was tried
     // and is slower: r1s)
     uint32_t peers = __ballot_sync(0xFFFFFFFFu, valid);
@@ -199,14 +218,14 @@ rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
   uint32_t gbase = 0;
 #pragma unroll
   for (int q = 0; q < RS_WARPS; ++q) gbase += (q < (int)w) ? wsum[q] : 0u;
-  gofs[tid] = (gbase + gincl - gt) + hist_scanned[(size_t)tid * nblk + blockIdx.x] - excl;
+  gofs[tid] = (gbase + gincl - gt) + hist_scanned[(size_t)tid * nblk + blk] - excl;
   __syncthreads();
 
 #pragma unroll
   for (int k = 0; k < RS_ITEMS; ++k) {
     const uint32_t li = w * RS_WARP_SPAN + k * 32 + lane;
     if (li < nvalid) {
-      const uint32_t d = (key[k] >> shift) & 0xFFu;
+      const uint32_t d = (key[k] >> shift) & dmask;
       const uint32_t lp = dbase[d] + cnt[w][d] + rank[k];
       skey[lp] = key[k];
       sval[lp] = vals_in[base + li];
@@ -218,7 +237,7 @@ rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
     const uint32_t lp = k * RS_THREADS + tid;
     if (lp < nvalid) {
       const uint32_t kk = skey[lp];
-      const uint32_t g = gofs[(kk >> shift) & 0xFFu] + lp;
+      const uint32_t g = gofs[(kk >> shift) & dmask] + lp;
       keys_out[g] = kk;
       vals_out[g] = sval[lp];
     }
@@ -253,9 +272,14 @@ scan_reduce_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ parti
   if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
 
-// single CTA: exclusive scan of the block partials (64-bit running sum for the grand total)
+// single CTA: exclusive scan of the block partials (64-bit running sum for the grand total).
+// With `st` set, the total is the frame's tile-instance count: it is checked against the capacity
+// of the instance buffers ON THE DEVICE (st->n_inst_eff = total if it fits, else 0 and the frame
+// is flagged: every later kernel then has nothing to do and the target stays untouched), which is
+// what lets the host enqueue the rest of the frame without reading the count.
 __global__ void __launch_bounds__(1024)
-scan_partials_kernel(uint32_t *__restrict__ partial, uint32_t np, unsigned long long *total_out) {
+scan_partials_kernel(uint32_t *__restrict__ partial, uint32_t np, unsigned long long *total_out,
+                     FrameStatus *st = nullptr, unsigned long long cap = 0) {
   __shared__ unsigned long long wsum[32];
   __shared__ unsigned long long carry_s;
   if (threadIdx.x == 0) carry_s = 0;
@@ -280,7 +304,15 @@ scan_partials_kernel(uint32_t *__restrict__ partial, uint32_t np, unsigned long 
     if (threadIdx.x == 1023) carry_s = carry + wb + incl;
     __syncthreads();
   }
-  if (threadIdx.x == 0 && total_out) *total_out = carry_s;
+  if (threadIdx.x == 0) {
+    if (total_out) *total_out = carry_s;
+    if (st) {
+      const bool fits = carry_s <= cap;
+      st->n_inst_eff = fits ? (unsigned int)carry_s : 0u;
+      st->overflow = fits ? 0u : 1u;
+      if (!fits) st->skipped += 1u;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(SC_THREADS)

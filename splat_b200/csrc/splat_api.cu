@@ -22,6 +22,7 @@
 #include "../../include/splat.h"
 #include "bin.cuh"
 #include "blend.cuh"
+#include "blend_float.cuh"
 #include "common.cuh"
 #include "project.cuh"
 #include "sort.cuh"
@@ -73,9 +74,20 @@ struct splat_ctx {
   double wait_limit_s = 30.0;                  // SPLAT_WAIT_LIMIT_S: bound of every host wait on the device
   uint32_t *d_fb = nullptr; size_t fb_cap = 0;
 
+  float4 *d_tap = nullptr; size_t tap_cap = 0; bool want_tap = false;   // float mode: un-quantised result per pixel (tests)
+
   // last frame
   int order_buf = 0;          // which vals[] holds the depth order
   bool have_frame = false, host_copy = false;
+  bool status_pending = false;   // a frame's status copy is in flight (status_ev)
+  bool retry_pending = false;    // a frame was skipped on the device (instance buffers too small) and not yet repeated
+  bool loads_valid = false;      // c->ranges describes the complete tile lists of the last frame
+  uint32_t skipped_seen = 0;
+  uint64_t frames_skipped = 0;
+  uint32_t geom[4] = {0, 0, 0, 0};   // W, H, row0, row1 of the last frame
+  FrameParams last_params{};
+  uint32_t *last_fb = nullptr;
+  cudaStream_t last_stream = nullptr;
   uint32_t retried = 0;
   uint64_t launches = 0, last_instances = 0, last_visible = 0, last_tiles = 0;
 };
@@ -107,9 +119,14 @@ int wait_done(splat_ctx *c, cudaEvent_t ev, cudaStream_t s, const char *what) {
       int rc = fail(c, SPLAT_ERR_CUDA, what, e);
       if (c->h_wd && c->h_wd[0]) {
         char buf[160];
-        std::snprintf(buf, sizeof buf, " [blend watchdog: block %u thread %u role %u slot %u chunk %u parity %u]", c->h_wd[1],
+        std::snprintf(buf, sizeof buf, " [blend watchdog: block %u thread %u role %u slot %u chunk %u parity %u; state:", c->h_wd[1],
                       c->h_wd[2], c->h_wd[3] >> 28, (c->h_wd[3] >> 20) & 0xFFu, c->h_wd[3] & 0xFFFFFu, c->h_wd[4]);
         c->err += buf;
+        for (uint32_t i = 0; i < c->h_wd[5] && i < (uint32_t)WD_WORDS - 8u; ++i) {
+          std::snprintf(buf, sizeof buf, " %08x", c->h_wd[8 + i]);
+          c->err += buf;
+        }
+        c->err += "]";
       }
       return rc;
     }
@@ -145,22 +162,22 @@ void dev_free(T *&p) {
 inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
 
 // stable LSD radix sort of (key, value) pairs on bits [0, bits); returns the buffer index
-// (0/1) that holds the result, or a negative error code (SPLAT_DEBUG_SYNC runs).  `n` sizes the grid; if n_ptr is set the kernels sort only the
-// first *n_ptr pairs (a device-side count <= n).
-int radix_sort(splat_ctx *c, cudaStream_t s, uint32_t *keys[2], uint32_t *vals[2], uint32_t n, int bits,
-               int cur = 0, const uint32_t *n_ptr = nullptr) {
-  if (n == 0) return cur;
-  const uint32_t nblk = cdiv(n, RS_BLOCK);
+// (0/1) that holds the result, or a negative error code (SPLAT_DEBUG_SYNC runs).  The kernels take
+// the pair count from *n_ptr (or n_fixed if n_ptr is null); `n_grid` -- the number of pairs the
+// launch is sized for -- must be an upper bound of it (the caller guarantees that on the device).
+int radix_sort(splat_ctx *c, cudaStream_t s, uint32_t *keys[2], uint32_t *vals[2], uint64_t n_grid, int bits,
+               int cur, const uint32_t *n_ptr, uint32_t n_fixed) {
+  const uint32_t grid = std::max(1u, std::min(cdiv(n_grid, RS_BLOCK), 1u << 20));
   for (int shift = 0; shift < bits; shift += 8) {
-    rs_hist_kernel<<<nblk, RS_THREADS, 0, s>>>(keys[cur], n_ptr, n, shift, c->hist, nblk);
-    rs_rowscan_kernel<<<256, RW_THREADS, 0, s>>>(c->hist, nblk, c->tot);
     const int nbits = std::min(8, bits - shift);
+    rs_hist_kernel<<<grid, RS_THREADS, 0, s>>>(keys[cur], n_ptr, n_fixed, shift, (1u << nbits) - 1u, c->hist);
+    rs_rowscan_kernel<<<256, RW_THREADS, 0, s>>>(c->hist, n_ptr, n_fixed, c->tot);
     if (nbits == 8)
-      rs_scatter_kernel<8><<<nblk, RS_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1],
-                                                       n_ptr, n, shift, 8, c->hist, c->tot, nblk);
+      rs_scatter_kernel<8><<<grid, RS_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1],
+                                                       n_ptr, n_fixed, shift, 8, c->hist, c->tot);
     else
-      rs_scatter_kernel<0><<<nblk, RS_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1],
-                                                       n_ptr, n, shift, nbits, c->hist, c->tot, nblk);
+      rs_scatter_kernel<0><<<grid, RS_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1],
+                                                       n_ptr, n_fixed, shift, nbits, c->hist, c->tot);
     c->launches += 2;
     LAUNCHED("radix sort pass (hist, rowscan, scatter)");
     cur ^= 1;
@@ -199,10 +216,14 @@ int ensure_instances(splat_ctx *c, uint64_t want) {
 }
 
 void free_scene(splat_ctx *c) {
+  cudaDeviceSynchronize();   // frames may still be in flight on a caller's stream
   dev_free(c->scene); dev_free(c->recs); dev_free(c->rects); dev_free(c->tcnt); dev_free(c->block_kept); dev_free(c->cnt); dev_free(c->offs);
   for (int k = 0; k < 2; ++k) { dev_free(c->keys[k]); dev_free(c->vals[k]); }
   c->n = 0;
   c->have_frame = false;
+  c->status_pending = false;
+  c->retry_pending = false;
+  c->loads_valid = false;
 }
 
 int alloc_scene(splat_ctx *c, uint64_t n) {
@@ -219,7 +240,7 @@ int alloc_scene(splat_ctx *c, uint64_t n) {
   c->n = (uint32_t)n;
   int rc = ensure_scratch(c, n);
   if (rc) return rc;
-  return ensure_instances(c, std::max<uint64_t>(c->cfg.max_instances, 1u << 20));
+  return ensure_instances(c, c->cfg.max_instances ? std::max<uint64_t>(c->cfg.max_instances, 4096u) : (1u << 20));
 }
 
 int make_params(splat_ctx *c, const splat_camera *cam, uint32_t W, uint32_t H, uint32_t row0,
@@ -263,17 +284,49 @@ int ilog2_ceil(uint32_t v) {
   return std::max(b, 1);
 }
 
+// What the host learnt from a finished frame's status block (copied to pinned memory behind the
+// blend kernel).  Called wherever the host has waited for the frame anyway, or finds it finished.
+void absorb_status(splat_ctx *c) {
+  const FrameStatus &fs = *c->h_status;
+  c->last_instances = fs.n_instances;
+  c->last_visible = fs.n_visible;
+  if (fs.skipped != c->skipped_seen) {          // a frame (or several) wanted more pairs than the buffers hold
+    c->frames_skipped += fs.skipped - c->skipped_seen;
+    c->skipped_seen = fs.skipped;
+    c->retry_pending = true;
+  }
+  c->status_pending = false;
+}
+void poll_status(splat_ctx *c) {
+  if (c->status_pending && cudaEventQuery(c->status_ev) == cudaSuccess) absorb_status(c);
+}
+
+struct Pass {
+  uint32_t rank_cut = 0;            // near cut: depth ranks below this get no instances (0 = complete lists)
+  const TileRect *only_box = nullptr;
+  bool only_failed = false;
+  bool sync_count = true;           // host reads the instance count mid-frame (exact grids, buffers grown on the spot)
+};
+
 // Second half of a frame on `s`: bin the Gaussians of depth rank >= rank_cut into tiles, sort the
-// instances by tile, blend.  rank_cut = 0 is the complete frame; rank_cut > 0 is the near-cut
-// pass (bin.cuh), after which h_status->n_failed says whether the complete pass must follow.
-int render_back(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cudaStream_t s, cudaEvent_t wait_ev,
-                int cur, const uint32_t *n_sorted, uint32_t rank_cut, const TileRect *only_box = nullptr, bool only_failed = false) {
+// instances by tile, blend.
+//   sync_count = true : the host waits for the instance count (one round trip), grows the buffers if
+//                       needed and sizes the launches exactly.  First frame of a target geometry,
+//                       near-cut frames, and the repeat of a skipped frame.
+//   sync_count = false: nothing blocks.  Launches are sized from the previous frame (+12.5%); the
+//                       kernels read the count from device memory, and a frame whose pairs do not
+//                       fit that bound blends NOTHING (status.overflow) and is repeated by the host.
+int bin_sort_blend(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cudaStream_t s, cudaEvent_t wait_ev,
+                   int cur, const uint32_t *n_sorted, const Pass &pass) {
   TileRect box;                      // tiles this pass bins into (stripe-local tile coordinates)
   box.x0 = 0; box.y0 = 0; box.x1 = 0xFFFF; box.y1 = 0xFFFF;
-  if (only_box) box = *only_box;
+  if (pass.only_box) box = *pass.only_box;
+  const uint32_t rank_cut = pass.rank_cut;
   const uint32_t n = c->n;
   const uint32_t T = P.tiles_x * P.tiles_y;
+  const bool flt = c->cfg.blend_mode == SPLAT_BLEND_FLOAT;
   if (T > c->ranges_cap) {
+    CU(cudaStreamSynchronize(s));
     dev_free(c->ranges);
     dev_free(c->units);
     dev_free(c->far_cnt);
@@ -287,12 +340,13 @@ int render_back(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cudaS
   {
     const size_t cells = (size_t)(P.tiles_x + 1) * (P.tiles_y + 1);   // not a function of T alone
     if (cells > c->far_cells_cap) {
+      CU(cudaStreamSynchronize(s));
       dev_free(c->far_diff);
       CU(dev_alloc(&c->far_diff, cells));
       c->far_cells_cap = cells;
     }
   }
-  // n_instances, n_visible, n_failed (n_sort, behind them, belongs to the first half)
+  // n_instances, n_visible, n_failed, fail box, n_cut (the fields behind them belong to the frame)
   CU(cudaMemsetAsync(c->d_status, 0, offsetof(FrameStatus, n_sort), s));
   const uint32_t *far = nullptr;
   if (rank_cut) {
@@ -306,74 +360,99 @@ int render_back(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cudaS
     LAUNCHED("far_cover / far_prefix");
     far = c->far_cnt;
   }
+  // no-round-trip frames: launches are sized for 1.125x the last count the host has seen (+64k); a
+  // frame that wants more is skipped on the device (overflow) and repeated with a round trip
+  const uint64_t n_bound = std::min<uint64_t>(c->inst_cap, c->last_instances + c->last_instances / 8 + 65536u);
   tile_count_kernel<<<cdiv(n, 256), 256, 0, s>>>(c->keys[cur], c->vals[cur], c->tcnt, c->cnt, n, n_sorted, rank_cut, c->d_status,
-                                                  only_box ? c->rects : nullptr, box);
+                                                  pass.only_box ? c->rects : nullptr, box);
   LAUNCHED("tile_count_kernel");
-  // exclusive scan cnt -> offs, grand total -> status.n_instances
+  // exclusive scan cnt -> offs; grand total -> status.n_instances, checked against the buffer
+  // capacity on the device (status.n_inst_eff / overflow)
   {
     const uint32_t np = std::max(1u, cdiv(n, SC_BLOCK));
     scan_reduce_kernel<<<np, SC_THREADS, 0, s>>>(c->cnt, c->partial, n);
-    scan_partials_kernel<<<1, 1024, 0, s>>>(c->partial, np, &c->d_status->n_instances);
+    scan_partials_kernel<<<1, 1024, 0, s>>>(c->partial, np, &c->d_status->n_instances, c->d_status,
+                                            pass.sync_count ? 0xFFFFFFFEull : (unsigned long long)n_bound);
     scan_apply_kernel<<<np, SC_THREADS, 0, s>>>(c->cnt, c->offs, c->partial, n);
     c->launches += 2;
     LAUNCHED("scan (tile counts)");
   }
   CU(cudaEventRecord(c->ev[EV_COUNT], s));
-  CU(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(FrameStatus), cudaMemcpyDeviceToHost, s));
-  CU(cudaEventRecord(c->status_ev, s));
-  { int rcw = wait_done(c, c->status_ev, s, "tile count (first half of the frame)"); if (rcw) return rcw; }   // host round trip: the instance count sizes the next launches
-  const uint64_t I = c->h_status->n_instances;
-  c->last_instances = I;
-  c->last_visible = c->h_status->n_visible;
+  uint64_t n_grid;                   // instances the launches below are sized for
+  if (pass.sync_count) {
+    CU(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(FrameStatus), cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(c->status_ev, s));
+    { int rcw = wait_done(c, c->status_ev, s, "tile count (first half of the frame)"); if (rcw) return rcw; }
+    const uint64_t I = c->h_status->n_instances;
+    c->last_instances = I;
+    c->last_visible = c->h_status->n_visible;
+    if (I >= 0xFFFFFFFEull) return fail(c, SPLAT_ERR_UNSUPPORTED, "more than 2^32-2 tile instances in one stripe");
+    if (I > c->inst_cap) {
+      int rc = ensure_instances(c, I);
+      if (rc) return rc;
+      c->retried += 1;
+    }
+    n_grid = I;
+  } else {
+    n_grid = n_bound;
+  }
   c->last_tiles = (uint64_t)T;
-  if (I > c->inst_cap) {
-    int rc = ensure_instances(c, I);
-    if (rc) return rc;
-    c->retried += 1;
-  }
-  int icur = 0;
-  if (I > 0) {
-    emit_instances_kernel<<<cdiv(n, 256), 256, 0, s>>>(c->vals[cur], c->rects, c->cnt, c->offs,
-                                                        c->ikeys[0], c->ivals[0], n, P.tiles_x, box);
-    LAUNCHED("emit_instances_kernel");
-  }
+  const uint32_t *n_eff = &c->d_status->n_inst_eff;
+  emit_instances_kernel<<<cdiv(n, 256), 256, 0, s>>>(c->vals[cur], c->rects, c->cnt, c->offs,
+                                                      c->ikeys[0], c->ivals[0], n, P.tiles_x, box, n_eff);
+  LAUNCHED("emit_instances_kernel");
   CU(cudaEventRecord(c->ev[EV_EMIT], s));
-  if (I > 0) icur = radix_sort(c, s, c->ikeys, c->ivals, (uint32_t)I, ilog2_ceil(T));
+  int icur = 0;
+  if (n_grid > 0) icur = radix_sort(c, s, c->ikeys, c->ivals, n_grid, ilog2_ceil(T), 0, n_eff, 0);
   if (icur < 0) return icur;
   CU(cudaEventRecord(c->ev[EV_TSORT], s));
   CU(cudaMemsetAsync(c->ranges, 0, (size_t)T * sizeof(uint2), s));
-  if (I > 0) {
-    tile_ranges_kernel<<<cdiv(I, 1024), 256, 0, s>>>(c->ikeys[icur], (uint32_t)I, c->ranges);
-    LAUNCHED("tile_ranges_kernel");
-  }
-  if (I > 0 || far) {
-    unit_order_kernel<<<1, 1024, 0, s>>>(c->ranges, T, c->units, c->n_units, &c->d_status->n_instances, far, c->d_status, P.tiles_x,
-                                         c->tile_failed, only_failed ? 1 : 0);   // heaviest first
-    LAUNCHED("unit_order_kernel");
-  }
+  tile_ranges_kernel<<<std::max(1u, std::min(cdiv(n_grid, 1024), 1u << 20)), 256, 0, s>>>(c->ikeys[icur], n_eff, c->ranges);
+  LAUNCHED("tile_ranges_kernel");
+  unit_order_kernel<<<1, 1024, 0, s>>>(c->ranges, T, c->units, c->n_units, &c->d_status->n_instances, far, c->d_status, P.tiles_x,
+                                       c->tile_failed, pass.only_failed ? 1 : 0, flt ? 1 : 0);   // heaviest first
+  LAUNCHED("unit_order_kernel");
   CU(cudaEventRecord(c->ev[EV_RANGES], s));
   if (wait_ev) CU(cudaStreamWaitEvent(s, wait_ev, 0));
-  if (I > 0) {
+  if (flt) {
+    blend_float_kernel<<<T, BF_THREADS, 0, s>>>(c->ranges, c->units, c->n_units, c->ivals[icur], c->recs, fb_rows_dev, P,
+                                                c->want_tap ? c->d_tap : nullptr, c->d_wd);
+    LAUNCHED("blend_float_kernel");
+  } else {
     blend_kernel<<<4 * T, BL_THREADS, BL_SMEM_BYTES, s>>>(c->ranges, c->units, c->n_units, c->ivals[icur], c->recs, fb_rows_dev, P,
                                                           far, c->d_status, c->tile_failed, c->d_wd);
     LAUNCHED("blend_kernel");
   }
   CU(cudaEventRecord(c->ev[EV_BLEND], s));
+  CU(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(FrameStatus), cudaMemcpyDeviceToHost, s));
+  CU(cudaEventRecord(c->status_ev, s));
+  c->status_pending = true;
   if (rank_cut) {
-    CU(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(FrameStatus), cudaMemcpyDeviceToHost, s));
-    CU(cudaEventRecord(c->status_ev, s));
     { int rcw = wait_done(c, c->status_ev, s, "near-cut pass (bin, sort, blend)"); if (rcw) return rcw; }   // did every pixel converge on the near lists?
+    c->status_pending = false;
   }
   return SPLAT_OK;
 }
 
 // Enqueue one frame on `s`, writing rows [row0,row1) into fb_rows_dev.  If wait_ev is set the
-// blend kernel waits for it (framebuffer upload on the copy stream).
-int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cudaStream_t s, cudaEvent_t wait_ev) {
+// blend kernel waits for it (framebuffer upload on the copy stream).  force_sync: use the
+// synchronous count path whatever the history says (the repeat of a skipped frame).
+int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cudaStream_t s, cudaEvent_t wait_ev,
+                 bool force_sync = false) {
   const uint32_t n = c->n;
   c->launches = 0;
+  c->retried = 0;
+  poll_status(c);
+  // Same target geometry as the last frame and its count known: nothing has to block.
+  const bool same_geom = c->have_frame && c->geom[0] == P.W && c->geom[1] == P.H && c->geom[2] == P.row0 && c->geom[3] == P.row1;
+  bool async = same_geom && !force_sync && !c->retry_pending && c->cut_frac >= 1024u && !c->cfg.sync_frames;
+  if (async && c->last_instances + c->last_instances / 8 + 65536u > c->inst_cap) {
+    // cudaFree / cudaMalloc wait for the frames in flight; rare (the buffers are grown with 25% headroom)
+    int rc = ensure_instances(c, c->last_instances + c->last_instances / 8 + 65536u);
+    if (rc) return rc;
+  }
   CU(cudaEventRecord(c->ev[EV_START], s));
-  CU(cudaMemsetAsync(c->d_status, 0, sizeof(FrameStatus), s));
+  CU(cudaMemsetAsync(c->d_status, 0, offsetof(FrameStatus, skipped), s));
   project_kernel<<<cdiv(n, 256), 256, 0, s>>>(c->scene, P, c->recs, c->keys[0], c->vals[0], c->rects, c->tcnt, c->block_kept);
   LAUNCHED("project_kernel");
   CU(cudaEventRecord(c->ev[EV_PROJECT], s));
@@ -391,7 +470,8 @@ int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cuda
     cur = 1;
     n_sorted = reinterpret_cast<const uint32_t *>(&c->d_status->n_sort);   // low word (n < 2^31)
   }
-  cur = radix_sort(c, s, c->keys, c->vals, n, 32, cur, n_sorted);
+  // (a stripe sorts only its survivors -- a device-side count; the CTAs beyond it exit at once)
+  cur = radix_sort(c, s, c->keys, c->vals, n, 32, cur, n_sorted, n);
   if (cur < 0) return cur;
   c->order_buf = cur;
   CU(cudaEventRecord(c->ev[EV_DSORT], s));
@@ -407,11 +487,15 @@ int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cuda
     const uint64_t keep = (c->last_visible * c->cut_frac + 1023u) / 1024u;
     if (keep < c->last_visible) rank_cut = (uint32_t)(c->last_visible - keep);
   }
-  int rc = render_back(c, P, fb_rows_dev, s, wait_ev, cur, n_sorted, rank_cut);
+  Pass pass;
+  pass.rank_cut = rank_cut;
+  pass.sync_count = !async;
+  int rc = bin_sort_blend(c, P, fb_rows_dev, s, wait_ev, cur, n_sorted, pass);
   if (rc) return rc;
   c->last_cut = rank_cut;
   c->last_failed = rank_cut ? c->h_status->n_failed : 0u;
   c->last_cut_instances = rank_cut ? c->h_status->n_cut : 0ull;
+  c->loads_valid = true;
   if (rank_cut && (c->h_status->n_failed != 0 || c->h_status->n_instances == 0)) {
     // The near lists were not enough for this view: bin + sort + blend again with ALL Gaussians,
     // restricted to the bounding box of the tiles that did not converge when that box is small
@@ -428,12 +512,45 @@ int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cuda
     if (!partial && c->cfg.near_cut < 0) c->cut_frac = std::min<uint32_t>(1024u, c->cut_frac * 2u);
     c->retried += 1;
     const uint64_t near_instances = fs.n_instances;
-    rc = render_back(c, P, fb_rows_dev, s, wait_ev, cur, n_sorted, 0, partial ? &fbx : nullptr, fs.n_instances != 0);
+    Pass again;
+    again.only_box = partial ? &fbx : nullptr;
+    again.only_failed = fs.n_instances != 0;
+    rc = bin_sort_blend(c, P, fb_rows_dev, s, wait_ev, cur, n_sorted, again);
     if (rc) return rc;
-    if (partial) c->last_instances += near_instances;     // both passes' instances were binned and sorted
+    if (partial) {
+      c->last_instances += near_instances;     // both passes' instances were binned and sorted
+      c->loads_valid = false;                   // c->ranges holds the box-restricted lists only
+    }
   }
   CU(cudaGetLastError());
   c->have_frame = true;
+  c->geom[0] = P.W; c->geom[1] = P.H; c->geom[2] = P.row0; c->geom[3] = P.row1;
+  c->last_params = P; c->last_fb = fb_rows_dev; c->last_stream = s;
+  return SPLAT_OK;
+}
+
+// Wait for the last enqueued frame; if it was skipped (its tile instances did not fit the buffers:
+// only possible on the no-round-trip path, when the count more than doubled in one frame), grow
+// the buffers and render it again on the synchronous path.  The skipped frame blended nothing, so
+// the target still holds what the caller put there.
+int finish_frame(splat_ctx *c) {
+  if (!c->have_frame) return SPLAT_OK;
+  if (c->status_pending) {
+    int rc = wait_done(c, c->status_ev, c->last_stream, "frame");
+    if (rc) return rc;
+    absorb_status(c);
+  }
+  for (int tries = 0; c->retry_pending && tries < 3; ++tries) {
+    c->retry_pending = false;
+    c->retried += 1;
+    int rc = ensure_instances(c, c->last_instances + c->last_instances / 4 + 65536u);
+    if (rc) return rc;
+    rc = render_frame(c, c->last_params, c->last_fb, c->last_stream, nullptr, true);
+    if (rc) return rc;
+    rc = wait_done(c, c->status_ev, c->last_stream, "frame (repeat)");
+    if (rc) return rc;
+    absorb_status(c);
+  }
   return SPLAT_OK;
 }
 
@@ -443,6 +560,8 @@ int upload_common(splat_ctx *c, uint64_t n) {
 }
 
 }  // namespace
+
+thread_local char g_create_error[256] = "";
 
 extern "C" {
 
@@ -459,7 +578,11 @@ void splat_config_default(splat_config *cfg) {
   cfg->max_instances = 0;
   cfg->blend_mode = SPLAT_BLEND_REFERENCE;
   cfg->near_cut = 0;
+  cfg->sync_frames = 0;
+  cfg->reserved = 0;
 }
+
+const char *splat_create_error(void) { return g_create_error; }
 
 int splat_create(splat_ctx **out, const splat_config *cfg) {
   if (!out) return SPLAT_ERR_INVALID;
@@ -467,13 +590,23 @@ int splat_create(splat_ctx **out, const splat_config *cfg) {
   splat_ctx *c = new (std::nothrow) splat_ctx();
   if (!c) return SPLAT_ERR_NOMEM;
   if (cfg) c->cfg = *cfg; else splat_config_default(&c->cfg);
-  auto bail = [&](int code) { splat_destroy(c); return code; };
-  if (c->cfg.tile != (uint32_t)TILE) return bail(SPLAT_ERR_UNSUPPORTED);
-  if (c->cfg.blend_mode != SPLAT_BLEND_REFERENCE) return bail(SPLAT_ERR_UNSUPPORTED);
-  if (c->cfg.near_cut < -1 || c->cfg.near_cut > 1024) return bail(SPLAT_ERR_INVALID);
+  g_create_error[0] = 0;
+  auto bail_msg = [&](int code, const char *what) {
+    const cudaError_t e = cudaGetLastError();
+    std::snprintf(g_create_error, sizeof g_create_error, "%s%s%s", what, e != cudaSuccess ? ": " : "", e != cudaSuccess ? cudaGetErrorString(e) : "");
+    splat_destroy(c);
+    return code;
+  };
+  auto bail = [&](int code) { return bail_msg(code, code == SPLAT_ERR_NOMEM ? "allocation failed" : "CUDA runtime call failed (is this an sm_100a device?)"); };
+  if (c->cfg.tile != (uint32_t)TILE) return bail_msg(SPLAT_ERR_UNSUPPORTED, "only 16-pixel tiles are built");
+  if (c->cfg.blend_mode != SPLAT_BLEND_REFERENCE && c->cfg.blend_mode != SPLAT_BLEND_FLOAT)
+    return bail_msg(SPLAT_ERR_UNSUPPORTED, "blend_mode must be SPLAT_BLEND_REFERENCE or SPLAT_BLEND_FLOAT");
+  if (c->cfg.near_cut < -1 || c->cfg.near_cut > 1024) return bail_msg(SPLAT_ERR_INVALID, "near_cut must be -1, 0 or 1..1024");
+  if (c->cfg.near_cut != 0 && c->cfg.blend_mode != SPLAT_BLEND_REFERENCE)
+    return bail_msg(SPLAT_ERR_UNSUPPORTED, "the near cut belongs to the reference blend (the float blend terminates early by itself)");
   // 0 = off (default: see DESIGN.md, known issue), -1 = automatic, 1..1024 = fixed fraction
   c->cut_frac = c->cfg.near_cut == 0 ? 1024u : (c->cfg.near_cut < 0 ? NEAR_CUT_DEFAULT : (uint32_t)c->cfg.near_cut);
-  if (!(c->cfg.lowpass >= 0.0f) || !std::isfinite(c->cfg.sample_offset)) return bail(SPLAT_ERR_INVALID);
+  if (!(c->cfg.lowpass >= 0.0f) || !std::isfinite(c->cfg.sample_offset)) return bail_msg(SPLAT_ERR_INVALID, "lowpass must be >= 0 and sample_offset finite");
   if (cudaSetDevice(c->cfg.device) != cudaSuccess) return bail(SPLAT_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(SPLAT_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(SPLAT_ERR_CUDA);
@@ -488,11 +621,13 @@ int splat_create(splat_ctx **out, const splat_config *cfg) {
   if (cudaFuncSetAttribute(far_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAR_SMEM_MAX) != cudaSuccess)
     return bail(SPLAT_ERR_CUDA);
   if (dev_alloc(&c->d_status, 1) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
+  if (cudaMemset(c->d_status, 0, sizeof(FrameStatus)) != cudaSuccess) return bail(SPLAT_ERR_CUDA);
   if (dev_alloc(&c->n_units, 1) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
   if (dev_alloc(&c->tot, 256) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
   if (cudaMallocHost(reinterpret_cast<void **>(&c->h_status), sizeof(FrameStatus)) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
-  if (cudaHostAlloc(reinterpret_cast<void **>(&c->h_wd), 8 * sizeof(uint32_t), cudaHostAllocMapped) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
-  std::memset(c->h_wd, 0, 8 * sizeof(uint32_t));
+  std::memset(c->h_status, 0, sizeof(FrameStatus));
+  if (cudaHostAlloc(reinterpret_cast<void **>(&c->h_wd), WD_WORDS * sizeof(uint32_t), cudaHostAllocMapped) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
+  std::memset(c->h_wd, 0, WD_WORDS * sizeof(uint32_t));
   if (cudaHostGetDevicePointer(reinterpret_cast<void **>(&c->d_wd), c->h_wd, 0) != cudaSuccess) return bail(SPLAT_ERR_CUDA);
   if (const char *e = std::getenv("SPLAT_DEBUG_SYNC")) c->debug_sync = e[0] == '1';
   if (const char *e = std::getenv("SPLAT_WAIT_LIMIT_S")) { const double v = std::atof(e); if (v > 0.0) c->wait_limit_s = v; }
@@ -505,7 +640,7 @@ void splat_destroy(splat_ctx *c) {
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_scene(c);
-  dev_free(c->hist); dev_free(c->tot); dev_free(c->partial); dev_free(c->ranges); dev_free(c->units); dev_free(c->far_cnt); dev_free(c->far_diff); dev_free(c->tile_failed); dev_free(c->n_units); dev_free(c->d_status); dev_free(c->d_fb);
+  dev_free(c->hist); dev_free(c->tot); dev_free(c->partial); dev_free(c->ranges); dev_free(c->units); dev_free(c->far_cnt); dev_free(c->far_diff); dev_free(c->tile_failed); dev_free(c->n_units); dev_free(c->d_status); dev_free(c->d_fb); dev_free(c->d_tap);
   for (int k = 0; k < 2; ++k) { dev_free(c->ikeys[k]); dev_free(c->ivals[k]); }
   if (c->h_status) cudaFreeHost(c->h_status);
   if (c->h_wd) cudaFreeHost(c->h_wd);
@@ -563,6 +698,18 @@ int splat_upload_aos(splat_ctx *c, const float *g59, uint64_t n) {
   return SPLAT_OK;
 }
 
+// a frame skipped on the device cannot be repeated behind the caller's back when the target is the
+// caller's device buffer (it may already have been consumed): report it, once, on the next call
+static int report_skipped(splat_ctx *c) {
+  poll_status(c);
+  if (!c->retry_pending) return SPLAT_OK;
+  c->retry_pending = false;
+  int rc = ensure_instances(c, c->last_instances + c->last_instances / 4 + 65536u);
+  if (rc) return rc;
+  return fail(c, SPLAT_ERR_RETRY, "the previous splat_render_device frame was not rendered (its tile instances did not fit the "
+                                  "buffers, which have now been grown; its target is untouched): render it again");
+}
+
 int splat_render_device(splat_ctx *c, const splat_camera *cam, void *fb_rows_dev, uint32_t W, uint32_t H,
                         uint32_t row0, uint32_t row1, void *stream) {
   if (!c) return SPLAT_ERR_INVALID;
@@ -572,8 +719,29 @@ int splat_render_device(splat_ctx *c, const splat_camera *cam, void *fb_rows_dev
   int rc = make_params(c, cam, W, H, row0, row1, &P);
   if (rc) return rc;
   CU(cudaSetDevice(c->cfg.device));
+  rc = report_skipped(c);
+  if (rc) return rc;
   c->host_copy = false;
   return render_frame(c, P, static_cast<uint32_t *>(fb_rows_dev), stream ? static_cast<cudaStream_t>(stream) : c->stream, nullptr);
+}
+
+// host-buffer frames: the call waits for the frame anyway, so a skipped frame is simply repeated
+static int host_frame(splat_ctx *c, const FrameParams &P, uint32_t *host_fb, size_t px, cudaEvent_t wait_ev) {
+  int rc = render_frame(c, P, c->d_fb, c->stream, wait_ev);
+  if (rc) { cudaStreamSynchronize(c->copy_stream); return rc; }
+  for (int attempt = 0;; ++attempt) {
+    CU(cudaEventRecord(c->ev[EV_D2H0], c->stream));
+    CU(cudaMemcpyAsync(host_fb, c->d_fb, px * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaEventRecord(c->ev[EV_D2H1], c->stream));
+    rc = wait_done(c, nullptr, c->stream, "frame (kernels + framebuffer download)");
+    if (rc) return rc;
+    if (c->status_pending) absorb_status(c);
+    if (!c->retry_pending || attempt >= 2) break;
+    rc = finish_frame(c);          // grows the buffers, renders the frame again (d_fb was left untouched)
+    if (rc) return rc;
+  }
+  c->host_copy = true;
+  return SPLAT_OK;
 }
 
 int splat_render_rows(splat_ctx *c, const splat_camera *cam, uint32_t *fb_rows, uint32_t W, uint32_t H,
@@ -585,6 +753,8 @@ int splat_render_rows(splat_ctx *c, const splat_camera *cam, uint32_t *fb_rows, 
   int rc = make_params(c, cam, W, H, row0, row1, &P);
   if (rc) return rc;
   CU(cudaSetDevice(c->cfg.device));
+  rc = report_skipped(c);
+  if (rc) return rc;
   const size_t px = (size_t)(row1 - row0) * W;
   if (px > c->fb_cap) {
     CU(cudaStreamSynchronize(c->stream));
@@ -597,14 +767,7 @@ int splat_render_rows(splat_ctx *c, const splat_camera *cam, uint32_t *fb_rows, 
   CU(cudaMemcpyAsync(c->d_fb, fb_rows, px * 4, cudaMemcpyHostToDevice, c->copy_stream));
   CU(cudaEventRecord(c->ev[EV_H2D1], c->copy_stream));
   CU(cudaEventRecord(c->h2d_done, c->copy_stream));
-  rc = render_frame(c, P, c->d_fb, c->stream, c->h2d_done);
-  if (rc) { cudaStreamSynchronize(c->copy_stream); return rc; }
-  CU(cudaEventRecord(c->ev[EV_D2H0], c->stream));
-  CU(cudaMemcpyAsync(fb_rows, c->d_fb, px * 4, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaEventRecord(c->ev[EV_D2H1], c->stream));
-  { int rcw = wait_done(c, nullptr, c->stream, "frame (kernels + framebuffer download)"); if (rcw) return rcw; }
-  c->host_copy = true;
-  return SPLAT_OK;
+  return host_frame(c, P, fb_rows, px, c->h2d_done);
 }
 
 int splat_render(splat_ctx *c, const splat_camera *cam, uint32_t *fb, uint32_t W, uint32_t H) {
@@ -620,6 +783,8 @@ int splat_render_cleared(splat_ctx *c, const splat_camera *cam, uint32_t *fb_out
   int rc = make_params(c, cam, W, H, 0, H, &P);
   if (rc) return rc;
   CU(cudaSetDevice(c->cfg.device));
+  rc = report_skipped(c);
+  if (rc) return rc;
   const size_t px = (size_t)W * H;
   if (px > c->fb_cap) {
     CU(cudaStreamSynchronize(c->stream));
@@ -634,13 +799,26 @@ int splat_render_cleared(splat_ctx *c, const splat_camera *cam, uint32_t *fb_out
     fill_u32_kernel<<<cdiv(px, 1024), 256, 0, c->stream>>>(c->d_fb, clear, px);
   }
   CU(cudaEventRecord(c->ev[EV_H2D1], c->stream));
-  rc = render_frame(c, P, c->d_fb, c->stream, nullptr);
+  return host_frame(c, P, fb_out, px, nullptr);
+}
+
+int splat_debug_render_float(splat_ctx *c, const splat_camera *cam, uint32_t *fb_inout, uint32_t W, uint32_t H, float *rgba) {
+  if (!c || !rgba) return SPLAT_ERR_INVALID;
+  if (c->cfg.blend_mode != SPLAT_BLEND_FLOAT) return fail(c, SPLAT_ERR_STATE, "context was not created with SPLAT_BLEND_FLOAT");
+  CU(cudaSetDevice(c->cfg.device));
+  const size_t px = (size_t)W * H;
+  if (px > c->tap_cap) {
+    CU(cudaDeviceSynchronize());
+    dev_free(c->d_tap);
+    CU(dev_alloc(&c->d_tap, px));
+    c->tap_cap = px;
+  }
+  CU(cudaMemset(c->d_tap, 0xFF, px * sizeof(float4)));   // NaN pattern = "pixel not touched"
+  c->want_tap = true;
+  const int rc = splat_render(c, cam, fb_inout, W, H);
+  c->want_tap = false;
   if (rc) return rc;
-  CU(cudaEventRecord(c->ev[EV_D2H0], c->stream));
-  CU(cudaMemcpyAsync(fb_out, c->d_fb, px * 4, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaEventRecord(c->ev[EV_D2H1], c->stream));
-  { int rcw = wait_done(c, nullptr, c->stream, "frame (kernels + framebuffer download)"); if (rcw) return rcw; }
-  c->host_copy = true;
+  CU(cudaMemcpy(rgba, c->d_tap, px * sizeof(float4), cudaMemcpyDeviceToHost));
   return SPLAT_OK;
 }
 
@@ -648,7 +826,15 @@ int splat_get_timings(splat_ctx *c, splat_timings *t) {
   if (!c || !t) return SPLAT_ERR_INVALID;
   if (!c->have_frame) return fail(c, SPLAT_ERR_STATE, "no frame rendered yet");
   CU(cudaSetDevice(c->cfg.device));
-  CU(cudaEventSynchronize(c->ev[EV_BLEND]));
+  if (c->status_pending) {
+    int rcw = wait_done(c, c->status_ev, c->last_stream, "frame");
+    if (rcw) return rcw;
+    absorb_status(c);
+  } else {
+    int rcw = wait_done(c, c->ev[EV_BLEND], c->last_stream, "frame");
+    if (rcw) return rcw;
+  }
+  { int rcs = report_skipped(c); if (rcs) return rcs; }
   std::memset(t, 0, sizeof(*t));
   auto el = [&](int a, int b) { float ms = 0.f; cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]); return ms; };
   t->project_ms = el(EV_START, EV_PROJECT);
@@ -670,14 +856,17 @@ int splat_get_timings(splat_ctx *c, splat_timings *t) {
   t->near_cut_rank = c->last_cut;
   t->near_cut_failed = c->last_failed;
   t->near_cut_instances = c->last_cut_instances;
+  t->frames_skipped = c->frames_skipped;
   return SPLAT_OK;
 }
 
 int splat_get_tile_loads(splat_ctx *c, uint32_t *per_tile, uint64_t cap, uint64_t *n_tiles) {
   if (!c || !per_tile || !n_tiles) return SPLAT_ERR_INVALID;
   if (!c->have_frame) return fail(c, SPLAT_ERR_STATE, "no frame rendered yet");
+  if (!c->loads_valid) return fail(c, SPLAT_ERR_STATE, "the last frame's second pass binned only part of the screen (near cut): no complete tile lists");
   CU(cudaSetDevice(c->cfg.device));
-  CU(cudaEventSynchronize(c->ev[EV_BLEND]));
+  { int rcw = wait_done(c, c->ev[EV_BLEND], c->last_stream, "frame"); if (rcw) return rcw; }
+  if (c->status_pending && cudaEventQuery(c->status_ev) == cudaSuccess) absorb_status(c);
   const uint64_t T = c->last_tiles, m = std::min<uint64_t>(cap, T);
   *n_tiles = T;
   if (c->last_instances == 0) { std::memset(per_tile, 0, m * sizeof(uint32_t)); return SPLAT_OK; }
@@ -734,7 +923,7 @@ int splat_debug_sort_pairs(splat_ctx *c, uint32_t *keys, uint32_t *vals, uint64_
   if (!rc) {
     cudaMemcpy(k[0], keys, n * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(v[0], vals, n * 4, cudaMemcpyHostToDevice);
-    const int cur = radix_sort(c, c->stream, k, v, (uint32_t)n, bits);
+    const int cur = radix_sort(c, c->stream, k, v, n, bits, 0, nullptr, (uint32_t)n);
     if (cur < 0) rc = cur;
     else {
       cudaStreamSynchronize(c->stream);
