@@ -247,7 +247,7 @@ def run_ours(args):
     from splat_b200 import stripes
     sc = stripes.broadcast_scene(make_scene(n) if rank == 0 else None, rank, dev)
     torch.cuda.empty_cache()
-    ctx = _lib.Context(device=local, lowpass=LOWPASS, near_cut=args.near_cut)
+    ctx = _lib.Context(device=local, lowpass=LOWPASS, near_cut=args.near_cut if world == 1 else 0)   # stripes: no host waits
     t0 = time.time()
     ctx.upload(sc)
     log(f"[bench] rank {rank}: scene uploaded in {time.time() - t0:.1f}s")
@@ -511,8 +511,8 @@ def main():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--cpu-row-step", type=int, default=0, help="CPU legs: rasterise every k-th tile stripe only (0/1 = whole frame)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--near-cut", type=int, default=0,
-                    help="splat_config.near_cut: 0 = off (default), -1 = automatic, 1..1024 = fixed fraction (experimental)")
+    ap.add_argument("--near-cut", type=int, default=-1,
+                    help="splat_config.near_cut: -1 = automatic (the library default), 0 = off, 1..1024 = fixed fraction")
     ap.add_argument("--equal-stripes", action="store_true", help="N > 1: equal tile-row stripes instead of load-balanced ones")
     args = ap.parse_args()
     capture_stdout()

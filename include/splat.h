@@ -70,10 +70,13 @@ typedef struct {
   uint32_t tile;           /* screen tile edge in pixels; only 16 is built                       */
   uint64_t max_instances;  /* initial capacity of the tile-instance buffers (0 = auto, grows)    */
   int32_t  blend_mode;     /* SPLAT_BLEND_*: 0 = the reference's quantised far->near blend (parity) */
-  int32_t  near_cut;       /* EXPERIMENTAL, off by default (known issue).  First bin + sort only the
-                            * nearest k/1024 of the Gaussians and redo the tiles that do not converge with all
-                            * of them (results identical either way): 0 = off, -1 = automatic (starts at 1/8,
-                            * doubles after a whole-frame fall-back), 1..1024 = fixed fraction */
+  int32_t  near_cut;       /* The reference blend reads only the nearest few hundred entries of a tile list (exact
+                            * early termination), so a frame first bins + sorts only the nearest k/1024 of the
+                            * Gaussians and redoes the tiles that do not converge on them with all of them.
+                            * Pixels are identical either way.  -1 (default) = automatic: starts at 1/8 once a
+                            * scene shows >= 200k visible Gaussians, doubles after a whole-frame fall-back;
+                            * 0 = off; 1..1024 = fixed fraction.  Near-cut frames read two status words on the
+                            * host per frame; frames without it need no host wait at all.                      */
   int32_t  sync_frames;    /* 1: read the tile-instance count on the host in the middle of every frame (exact
                             * launch sizes, one round trip per frame).  0 (default): only the first frame of a
                             * target geometry does; later frames are enqueued without any host wait            */
@@ -178,6 +181,36 @@ int splat_get_timings(splat_ctx *ctx, splat_timings *out);
  * multi-GPU driver sums them per tile row to place stripe boundaries.  Writes
  * min(cap, n_tiles) entries and returns the stripe's tile count in *n_tiles. */
 int splat_get_tile_loads(splat_ctx *ctx, uint32_t *per_tile, uint64_t cap, uint64_t *n_tiles);
+
+/* ---- Multi-GPU.  The frame shards by horizontal stripes of whole tile rows; the scene
+ * is replicated (one broadcast at upload); the only per-frame exchange is ONE gather of the
+ * stripes' rows into the root's frame (grouped ncclSend / ncclRecv over NVLink, straight from and
+ * into the render targets).  The reference has no counterpart: its only parallelism is euc's
+ * row-group threading.  libnccl.so.2 is loaded on first use; single-GPU callers never need it.
+ *
+ * (1) One process, several GPUs -- what a Rust caller of render_to_buffer gets by listing devices:
+ * splat_create_multi returns a GROUP context that owns one ordinary context per device and their
+ * communicators (ncclCommInitAll).  splat_upload_soa/aos upload to devices[0] and broadcast the
+ * packed scene; splat_render / splat_render_cleared render every member's stripe concurrently,
+ * gather, and return the frame; the stripe boundaries are re-cut from the members' measured frame
+ * times; splat_get_timings reports the slowest member per stage.  Pixels are byte-identical to a
+ * single-device render for every partition.  cfg.reserved = 1 keeps equal stripes. */
+int splat_create_multi(splat_ctx **out, const splat_config *cfg, const int32_t *devices, int32_t n_devices);
+/* stripe rows [bounds[2k], bounds[2k+1]) of member k for the next frame */
+int splat_group_get_bounds(splat_ctx *group, uint32_t *bounds, int32_t cap_ranks, int32_t *n_ranks);
+
+/* (2) One process per GPU (a torchrun-style launcher): rank 0 makes the id, the launcher carries its
+ * 128 bytes to the other ranks, every rank joins with its own ordinary context. */
+#define SPLAT_UNIQUE_ID_BYTES 128
+int splat_comm_unique_id(void *id128);
+int splat_comm_init_rank(splat_ctx *ctx, const void *id128, int32_t n_ranks, int32_t rank);
+/* C0: `root` has uploaded n Gaussians; every other rank receives the packed device scene. */
+int splat_comm_broadcast_scene(splat_ctx *ctx, int32_t root, uint64_t n);
+/* C1: rows [bounds[2r], bounds[2r+1]) of rank r's W x H device frame -> the same rows of root's frame,
+ * enqueued on `stream` (NULL = the context's) behind the render that wrote them.  bounds: 2 * n_ranks
+ * entries, contiguous, ordered, covering [0, H). */
+int splat_gather_stripes(splat_ctx *ctx, void *fb_dev, uint32_t W, uint32_t H, const uint32_t *bounds, int32_t root,
+                         void *stream);
 
 /* Pin / unpin a caller-owned host buffer (cudaHostRegister) so that the framebuffer copies of
  * splat_render run at full PCIe rate; e.g. the Rust shim pins `color.raw_mut()` once. */

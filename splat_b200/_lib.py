@@ -22,7 +22,9 @@ EXPORTS = ["splat_abi_version", "splat_config_default", "splat_create", "splat_c
            "splat_last_error", "splat_upload_soa", "splat_upload_aos", "splat_render", "splat_render_cleared",
            "splat_render_rows", "splat_render_device", "splat_get_timings", "splat_get_tile_loads", "splat_pin_host",
            "splat_unpin_host", "splat_debug_project", "splat_debug_read_order",
-           "splat_debug_sort_pairs", "splat_debug_blend_stats", "splat_debug_render_float"]
+           "splat_debug_sort_pairs", "splat_debug_blend_stats", "splat_debug_render_float",
+           "splat_create_multi", "splat_group_get_bounds", "splat_comm_unique_id", "splat_comm_init_rank",
+           "splat_comm_broadcast_scene", "splat_gather_stripes"]
 
 
 class SplatConfig(C.Structure):
@@ -93,6 +95,12 @@ def load():
     L.splat_debug_sort_pairs.argtypes = [vp, vp, vp, C.c_uint64, C.c_int]
     L.splat_debug_blend_stats.argtypes = [vp, vp, C.c_int]
     L.splat_debug_render_float.argtypes = [vp, C.POINTER(SplatCamera), vp, C.c_uint32, C.c_uint32, vp]
+    L.splat_create_multi.argtypes = [C.POINTER(vp), C.POINTER(SplatConfig), C.POINTER(C.c_int32), C.c_int32]
+    L.splat_group_get_bounds.argtypes = [vp, vp, C.c_int32, C.POINTER(C.c_int32)]
+    L.splat_comm_unique_id.argtypes = [vp]
+    L.splat_comm_init_rank.argtypes = [vp, vp, C.c_int32, C.c_int32]
+    L.splat_comm_broadcast_scene.argtypes = [vp, C.c_int32, C.c_uint64]
+    L.splat_gather_stripes.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_int32, vp]
     for name in EXPORTS:
         getattr(L, name)  # AttributeError if the .so does not export it
     _lib = L
@@ -123,20 +131,52 @@ def _fp(a):
 class Context:
     """Owns one splat_ctx (one GPU)."""
 
-    def __init__(self, device=0, lowpass=0.3, y_down=0, zclip_mode=1, sample_offset=0.5, max_instances=0, near_cut=0,
-                 blend_mode=SPLAT_BLEND_REFERENCE, sync_frames=0):
+    def __init__(self, device=0, lowpass=0.3, y_down=0, zclip_mode=1, sample_offset=0.5, max_instances=0, near_cut=-1,
+                 blend_mode=SPLAT_BLEND_REFERENCE, sync_frames=0, devices=None, equal_stripes=False):
+        """devices: a list of CUDA ordinals makes this a GROUP context (splat_create_multi): one process,
+        several GPUs, stripes cut and gathered inside the library."""
         self.L = load()
         cfg = SplatConfig()
         self.L.splat_config_default(C.byref(cfg))
         cfg.device, cfg.lowpass, cfg.y_down = device, lowpass, y_down
         cfg.zclip_mode, cfg.sample_offset, cfg.max_instances = zclip_mode, sample_offset, max_instances
-        cfg.near_cut, cfg.blend_mode, cfg.sync_frames = near_cut, blend_mode, sync_frames
+        cfg.near_cut, cfg.blend_mode, cfg.sync_frames = (near_cut if blend_mode == SPLAT_BLEND_REFERENCE or near_cut > 0 else 0), blend_mode, sync_frames
+        cfg.reserved = 1 if equal_stripes else 0
         self.cfg = cfg
         self.h = C.c_void_p()
-        rc = self.L.splat_create(C.byref(self.h), C.byref(cfg))
+        self.devices = list(devices) if devices is not None else None
+        if self.devices is None:
+            rc = self.L.splat_create(C.byref(self.h), C.byref(cfg))
+        else:
+            arr = (C.c_int32 * len(self.devices))(*self.devices)
+            rc = self.L.splat_create_multi(C.byref(self.h), C.byref(cfg), arr, len(self.devices))
         if rc:
             raise SplatError(rc, "splat_create failed: " + self.L.splat_create_error().decode())
         self.n = 0
+
+    # ---- one process per GPU: communicator owned by the context (include/splat.h, multi-GPU (2))
+    def unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self._check(self.L.splat_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, n_ranks: int, rank: int):
+        self._check(self.L.splat_comm_init_rank(self.h, C.create_string_buffer(unique_id, 128), n_ranks, rank))
+
+    def broadcast_scene(self, root: int, n: int):
+        self._check(self.L.splat_comm_broadcast_scene(self.h, root, n))
+        self.n = n
+
+    def gather_stripes(self, fb_dev_ptr: int, W: int, H: int, bounds, root=0, stream=0):
+        flat = (C.c_uint32 * (2 * len(bounds)))(*[int(v) for b in bounds for v in b])
+        self._check(self.L.splat_gather_stripes(self.h, fb_dev_ptr, W, H, flat, root, stream or None))
+
+    def group_bounds(self):
+        n = C.c_int32()
+        self._check(self.L.splat_group_get_bounds(self.h, None, 0, C.byref(n)))
+        arr = (C.c_uint32 * (2 * n.value))()
+        self._check(self.L.splat_group_get_bounds(self.h, arr, n.value, C.byref(n)))
+        return [(int(arr[2 * k]), int(arr[2 * k + 1])) for k in range(n.value)]
 
     def _check(self, rc):
         if rc:

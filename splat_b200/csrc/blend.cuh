@@ -433,6 +433,18 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
   const uint32_t tx0 = tile_x * TILE, ty0 = (P.tile_y0 + tile_y) * TILE;
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+  // The mbarriers are initialised ONCE per CTA and made visible by a CTA-wide barrier in which every
+  // thread takes part, before the spare warps of a split unit leave.  Later suffix attempts do not
+  // touch them again: chunk numbers -- hence slots, owners and phase parities -- simply run on
+  // (cbase).  Invalidating and re-initialising the barriers between attempts, with other warps
+  // already polling for the next attempt's barrier, dead-locked about one unit in 10^4 on frames
+  // with thousands of short truncated lists (round-2 hunt, profiles/r2_near_cut_hang.txt).
+  if (tid < BL_SLOTS) {
+    mbar_init(&S.full[tid], 1);
+    mbar_init(&S.empty[tid], 1);
+  }
+  if (tid == 0) S.giveup = 0;
+  __syncthreads();
   if (w >= BL_PRODUCER_THREADS / 32 + ng) return;   // split units: the spare consumer warps have nothing to do
   const uint32_t nsync = BL_PRODUCER_THREADS + 32u * ng;   // threads that take part in this unit
   const f32x2 NZ = P.nz2;
@@ -444,7 +456,7 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
   // repeated with the full lists (splat_api.cu).
   const bool truncated = far_cnt != nullptr && far_cnt[tile] != 0u;
   bool gave_up = false;
-  if (tid == 0) S.giveup = 0;
+  uint32_t cbase = 0;   // chunks this thread's team handed over in earlier attempts
 
   // ---- suffix attempts (see "Exact early termination" in the header) ----
   // Attempt k composites only the last `suffix` list entries, starting every pixel from BOTH
@@ -470,10 +482,6 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
   }
   const WdDump wdd{reinterpret_cast<const uint32_t *>(&S.full[0]),
                    (uint32_t)((sizeof(S.full) + sizeof(S.empty) + sizeof(S.hdr) + sizeof(S.info) + sizeof(S.trace)) / 4)};
-  if (tid < BL_SLOTS) {
-    mbar_init(&S.full[tid], 1);
-    mbar_init(&S.empty[tid], 1);
-  }
   unit_sync(nsync);
 
   if (w < BL_PRODUCER_THREADS / 32) {
@@ -498,7 +506,8 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
       syh[q] = (float)(ty0 + 8u * q + 7u) + P.sample_off;
     }
     const uint32_t lt_mask = (1u << lane) - 1u;
-    uint32_t seq = 0;    // list entries of this team handed out so far (both producers count alike)
+    uint32_t seq = cbase * BL_CH;   // list entries of this team handed out so far, counted on from the earlier
+                                    // attempts in whole chunks (both producers count alike)
     uint32_t nout = 0;   // entries written into the chunk this producer is filling
 #ifdef SPLAT_STATS
     uint32_t st_eval = 0, st_out = 0, st_pix = 0, st_cand = 0, st_lanes = 0;
@@ -684,6 +693,7 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
         }
       }
       WD_TRACE(6, seq);
+      cbase = chunk + 1u;
     }
   } else {
     // ============================== CONSUMERS ==============================
@@ -744,7 +754,7 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
       hr = hg = hb = pk1(1.0f);            // byte 255: div255(255) == 1
     }
 
-    for (uint32_t chunk = 0;; ++chunk) {
+    for (uint32_t chunk = cbase;; ++chunk) {
       const uint32_t slot = (gl << d_log) + (chunk & d_mask);
       WD_TRACE(7, chunk);
       mbar_wait<SPLAT_WAIT_CONSUMER>(&S.full[slot], (chunk >> d_log) & 1u, n_units, wd,
@@ -786,7 +796,7 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.empty[slot]);
-      if (h & 0x100u) break;
+      if (h & 0x100u) { cbase = chunk + 1u; break; }
     }
     // truncated list: an inside pixel that none of its quads covers may be covered by a cut one
     const bool unknown = truncated && __any_sync(0xFFFFFFFFu, (inside0 && last0 == 0xFFFFFFFFu) ||
@@ -806,10 +816,6 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
   if (!any_fail) break;
   if (whole || S.giveup) { gave_up = true; break; }     // only possible for a truncated list
   suffix = (suffix > 0x10000000u) ? 0xFFFFFFFFu : suffix * BL_SUFFIX_GROWTH;
-  if (tid < BL_SLOTS) {
-    mbar_inval(&S.full[tid]);
-    mbar_inval(&S.empty[tid]);
-  }
   }   // attempts
 
   if (gave_up && tid == 0) {

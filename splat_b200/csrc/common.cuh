@@ -9,11 +9,13 @@ constexpr int TILE = 16;                 // screen tile edge (pixels)
 constexpr int SCENE_PLANES = 10;         // float4 planes per Gaussian in the device scene
 constexpr uint32_t KEY_CULLED = 0xFFFFFFFFu;
 
-// Device scene layout (HBM, written once per upload by pack_scene_kernel):
-//   plane 0      : (x, y, z, opacity)
-//   planes 1..9  : 36 floats = cov3d[9] row-major followed by sh[0..26] (SH degrees 0..2)
+// Device scene layout (HBM, written once per upload by pack_scene_kernel), 160 B per Gaussian:
+//   plane 0      : (x, y, z, cov3d[8])
+//   planes 1..2  : cov3d[0..7] (row-major)        -- planes 0-2 are all the stripe pre-pass reads
+//   plane 3      : (opacity, sh[0], sh[1], sh[2])
+//   planes 4..9  : sh[3..26] (SH degrees 1..2)
 // Each plane is a dense float4[N] array, so a warp reading plane k for 32 consecutive
-// Gaussians issues one fully coalesced 512-byte request.  160 B per Gaussian.
+// Gaussians issues one fully coalesced 512-byte request.
 
 // Everything the kernels need to know about one frame; passed by value (__grid_constant__).
 struct FrameParams {

@@ -47,8 +47,35 @@ SPLAT_DEVINL void cov3d_from_rot_scale(const float4 q /* i,j,k,w */, const float
       C[r * 3 + qd] = (RS[r][0] * R[qd][0] + RS[r][1] * R[qd][1]) + RS[r][2] * R[qd][2];
 }
 
+// Device scene layout (common.cuh): plane 0 = (x, y, z, cov3d[8]), planes 1-2 = cov3d[0..7],
+// plane 3 = (opacity, sh[0..2]), planes 4-9 = sh[3..26].  The first three planes (48 B) are all
+// the geometry the stripe pre-pass needs.  f[0..8] = cov3d row-major, f[9..35] = sh[0..26].
+SPLAT_DEVINL void store_scene(float4 *__restrict__ scene, uint32_t n, uint32_t i, float x, float y, float z, float op,
+                              const float f[36]) {
+  scene[i] = make_float4(x, y, z, f[8]);
+  scene[(size_t)1 * n + i] = make_float4(f[0], f[1], f[2], f[3]);
+  scene[(size_t)2 * n + i] = make_float4(f[4], f[5], f[6], f[7]);
+  scene[(size_t)3 * n + i] = make_float4(op, f[9], f[10], f[11]);
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+    scene[(size_t)(k + 4) * n + i] = make_float4(f[12 + 4 * k], f[13 + 4 * k], f[14 + 4 * k], f[15 + 4 * k]);
+}
+// the reverse: all ten planes of Gaussian ii (ten independent 16-byte loads in flight)
+SPLAT_DEVINL void load_scene(const float4 *__restrict__ scene, uint32_t n, uint32_t ii, float4 &p0, float &op, float f[36]) {
+  float4 v[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) v[k] = __ldg(&scene[(size_t)k * n + ii]);
+  p0 = v[0];
+  f[0] = v[1].x; f[1] = v[1].y; f[2] = v[1].z; f[3] = v[1].w;
+  f[4] = v[2].x; f[5] = v[2].y; f[6] = v[2].z; f[7] = v[2].w;
+  f[8] = v[0].w;
+  op = v[3].x; f[9] = v[3].y; f[10] = v[3].z; f[11] = v[3].w;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { f[12 + 4 * k] = v[4 + k].x; f[13 + 4 * k] = v[4 + k].y; f[14 + 4 * k] = v[4 + k].z; f[15 + 4 * k] = v[4 + k].w; }
+}
+
 // One thread per Gaussian.  Inputs are the raw GaussianList arrays (gaussians.rs:408-416)
-// already on the device; output is the 10-plane float4 scene (common.cuh).
+// already on the device; output is the 10-plane float4 scene.
 __global__ void __launch_bounds__(256)
 pack_scene_kernel(const float4 *__restrict__ pos4, const float *__restrict__ scale3,
                   const float *__restrict__ opacity, const float4 *__restrict__ rot,
@@ -62,10 +89,7 @@ pack_scene_kernel(const float4 *__restrict__ pos4, const float *__restrict__ sca
   const float *sh = sh48 + 48 * (size_t)i;
 #pragma unroll
   for (int k = 0; k < 27; ++k) f[9 + k] = sh[k];
-  scene[i] = make_float4(p.x, p.y, p.z, opacity[i]);
-#pragma unroll
-  for (int k = 0; k < 9; ++k)
-    scene[(size_t)(k + 1) * n + i] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+  store_scene(scene, n, i, p.x, p.y, p.z, opacity[i], f);
 }
 
 // AoS variant for Pipeline01's Vec<Gaussian>: 59 floats per Gaussian (include/splat.h).
@@ -78,10 +102,7 @@ pack_scene_aos_kernel(const float *__restrict__ g59, float4 *__restrict__ scene,
   cov3d_from_rot_scale(make_float4(g[7], g[8], g[9], g[10]), g[3], g[4], g[5], f);
 #pragma unroll
   for (int k = 0; k < 27; ++k) f[9 + k] = g[11 + k];
-  scene[i] = make_float4(g[0], g[1], g[2], g[6]);
-#pragma unroll
-  for (int k = 0; k < 9; ++k)
-    scene[(size_t)(k + 1) * n + i] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+  store_scene(scene, n, i, g[0], g[1], g[2], g[6], f);
 }
 
 // ---------------------------------------------------------------- K1: project
@@ -108,38 +129,99 @@ struct TileRect {
 };
 static_assert(sizeof(TileRect) == 8, "TileRect is packed as uint2");
 
-// One thread per Gaussian.  Geometry phase: 4 coalesced float4 loads (position/opacity, cov3d),
-// view transform, cov2d, conic, 3-sigma extents, z clip, tile rectangle.  Colour phase: 6 more
-// float4 loads (SH degrees 0..2) and the SH evaluation.  Out: 48 B record + 4 B key + 4 B index
-// + 8 B rect + 4 B tile count.  Algorithmic bytes: 160 in + 68 out = 228 B per Gaussian.
-//
-// Stripe renders (multi-GPU, P.stripe_cull): a Gaussian whose quad cannot touch this rank's
-// stripe is dropped after the geometry phase -- no SH loads, key = KEY_CULLED -- and
-// block_kept[] counts the survivors per CTA so that compact_pairs_kernel can squeeze the
-// (key, index) pairs before the depth sort: each rank then sorts only what its stripe sees.
+// ---------------------------------------------------------------- stripe pre-pass (multi-GPU)
+// A rank that renders one stripe of the screen needs only the Gaussians whose 3-sigma quad can
+// reach its rows.  One thread per Gaussian reads the 48 B of geometry (planes 0-2), repeats the
+// y half of the projection -- view transform, the yy entry of the 2D covariance, NDC y -- in
+// exactly the operations of project_kernel, and votes: bit = 1 if rows [row0, row1) widened by one
+// pixel can intersect the quad.  A superset by construction (same arithmetic plus the margin); the
+// exact decision is made by project_kernel, which then runs densely over the survivors only.
+// Out: one ballot word per warp and the survivor count per CTA.
 __global__ void __launch_bounds__(256)
-project_kernel(const float4 *__restrict__ scene, const __grid_constant__ FrameParams P,
-               Rec *__restrict__ recs, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
-               uint2 *__restrict__ rects, uint32_t *__restrict__ tcnt, uint32_t *__restrict__ block_kept) {
+stripe_cull_kernel(const float4 *__restrict__ scene, const __grid_constant__ FrameParams P,
+                   uint32_t *__restrict__ mask, uint32_t *__restrict__ block_kept) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t n = P.n;
   const bool valid = i < n;
-  const uint32_t ii = valid ? i : n - 1u;     // out-of-range threads recompute the last Gaussian, store nothing
+  const uint32_t ii = valid ? i : n - 1u;
   const float4 p0 = __ldg(&scene[ii]);
+  const float4 c0 = __ldg(&scene[(size_t)1 * n + ii]), c1 = __ldg(&scene[(size_t)2 * n + ii]);
+  const float C3[9] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, p0.w};
+  const float *V = P.view;
+  float pc[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    pc[r] = ((V[0 * 4 + r] * p0.x + V[1 * 4 + r] * p0.y) + V[2 * 4 + r] * p0.z) + V[3 * 4 + r];
+  const float zv = pc[2];
+  const float jd = __fdiv_rn(P.focal, zv);
+  const float T1[3] = {V[0 * 4 + 1] * jd, V[1 * 4 + 1] * jd, V[2 * 4 + 1] * jd};
+  float X1[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) X1[k] = (T1[0] * C3[k * 3 + 0] + T1[1] * C3[k * 3 + 1]) + T1[2] * C3[k * 3 + 2];
+  const float m22 = ((X1[0] * T1[0] + X1[1] * T1[1]) + X1[2] * T1[2]) + P.lowpass;
+  const float hy = 3.0f * __fsqrt_rn(m22);
+  const float *Pm = P.proj;
+  const float ps1 = ((Pm[0 * 4 + 1] * pc[0] + Pm[1 * 4 + 1] * pc[1]) + Pm[2 * 4 + 1] * pc[2]) + Pm[3 * 4 + 1] * pc[3];
+  const float ps2 = ((Pm[0 * 4 + 2] * pc[0] + Pm[1 * 4 + 2] * pc[1]) + Pm[2 * 4 + 2] * pc[2]) + Pm[3 * 4 + 2] * pc[3];
+  const float ps3 = ((Pm[0 * 4 + 3] * pc[0] + Pm[1 * 4 + 3] * pc[1]) + Pm[2 * 4 + 3] * pc[2]) + Pm[3 * 4 + 3] * pc[3];
+  const float ndy = __fdiv_rn(ps1, ps3), ndz = __fdiv_rn(ps2, ps3);
+  const float cyp = ((P.ysign * ndy) * 0.5f + 0.5f) * (float)P.H;
+  bool zok;
+  if (P.zclip_mode == 0) zok = (ndz >= 0.0f && ndz < 1.0f);
+  else if (P.zclip_mode == 1) zok = (ndz >= -1.0f && ndz < 1.0f);
+  else zok = true;
+  bool keep = valid && zok && finitef(zv) && finitef(hy) && finitef(cyp) && fabsf(cyp) <= 1e9f;
+  if (keep) {
+    const double off = (double)P.sample_off;
+    const double sly = 2.0 + 1e-6 * (fabs((double)cyp) + (double)hy);     // project_kernel's slack + one pixel
+    const double y0 = floor((double)cyp - (double)hy - off - sly), y1 = ceil((double)cyp + (double)hy - off + sly);
+    keep = y1 >= (double)P.row0 && y0 < (double)P.row1;
+  }
+  const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
+  if ((threadIdx.x & 31u) == 0u && (i >> 5) < (n + 31u) / 32u) mask[i >> 5] = bal;
+  const int kept = __syncthreads_count(keep);
+  if (threadIdx.x == 0) block_kept[blockIdx.x] = (uint32_t)kept;
+}
+
+// surv[block_off[b] + rank] = i for every voted Gaussian, in index order (the stable depth sort's
+// tie-break is the input order).  CTA b owns the 256 Gaussians stripe_cull_kernel's CTA b voted on.
+__global__ void __launch_bounds__(256)
+compact_idx_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ block_off,
+                   uint32_t *__restrict__ surv, uint32_t n) {
+  __shared__ uint32_t wcnt[8];
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x, lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  const uint32_t bal = (i - lane) < n ? mask[i >> 5] : 0u;
+  if (lane == 0) wcnt[w] = __popc(bal);
+  __syncthreads();
+  uint32_t before = 0;
+#pragma unroll
+  for (uint32_t q = 0; q < 8u; ++q) before += (q < w) ? wcnt[q] : 0u;
+  if ((bal >> lane) & 1u) surv[block_off[blockIdx.x] + before + __popc(bal & ((1u << lane) - 1u))] = i;
+}
+
+// K1.  One thread per Gaussian (SURV = false: all of them; SURV = true: the j-th survivor of the
+// stripe pre-pass, `n_surv` of them, a device-side count).  Ten coalesced (or, for survivors,
+// gathered) float4 loads, view transform, cov2d, conic, 3-sigma extents, z clip, tile rectangle,
+// SH colour.  Out: 48 B record + 8 B tile rect + 4 B tile count (by Gaussian index) and the
+// (depth key, index) pair (by thread index: a stripe's pairs are dense and in index order).
+// Algorithmic bytes: 160 in + 68 out = 228 B per Gaussian.
+template <bool SURV>
+__global__ void __launch_bounds__(256)
+project_kernel(const float4 *__restrict__ scene, const __grid_constant__ FrameParams P,
+               Rec *__restrict__ recs, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
+               uint2 *__restrict__ rects, uint32_t *__restrict__ tcnt,
+               const uint32_t *__restrict__ surv, const uint32_t *__restrict__ n_surv) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n = P.n;
+  const uint32_t count = SURV ? *n_surv : n;
+  const bool valid = j < count;
+  if (SURV && blockIdx.x * blockDim.x >= count) return;
+  const uint32_t i = valid ? (SURV ? __ldg(&surv[j]) : j) : n - 1u;   // out-of-range threads recompute the last Gaussian, store nothing
+  float4 p0;
+  float op;
   float f[36];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const float4 v = __ldg(&scene[(size_t)(k + 1) * n + ii]);
-    f[4 * k] = v.x; f[4 * k + 1] = v.y; f[4 * k + 2] = v.z; f[4 * k + 3] = v.w;
-  }
-  if (!P.stripe_cull) {   // full-frame renders need the colour of (almost) everything: all loads in flight at once
-#pragma unroll
-    for (int k = 3; k < 9; ++k) {
-      const float4 v = __ldg(&scene[(size_t)(k + 1) * n + ii]);
-      f[4 * k] = v.x; f[4 * k + 1] = v.y; f[4 * k + 2] = v.z; f[4 * k + 3] = v.w;
-    }
-  }
-  const float *C3 = f;        // cov3d row-major (f[0..8]); f[9..11] = sh[0..2]
+  load_scene(scene, n, i, p0, op, f);
+  const float *C3 = f;        // cov3d row-major (f[0..8])
   const float *sh = f + 9;    // sh[0..26]
   const float *V = P.view;
 
@@ -188,10 +270,8 @@ project_kernel(const float4 *__restrict__ scene, const __grid_constant__ FramePa
   const float ndx = __fdiv_rn(ps[0], ps[3]), ndy = __fdiv_rn(ps[1], ps[3]), ndz = __fdiv_rn(ps[2], ps[3]);
   const float cxp = (ndx * 0.5f + 0.5f) * (float)P.W;
   const float cyp = ((P.ysign * ndy) * 0.5f + 0.5f) * (float)P.H;
-  const float op = p0.w;
 
   // visibility: euc's z clip on the centre (all four corners share z) + degeneracy guard
-  // (everything except the colour, which the second phase adds)
   bool zok;
   if (P.zclip_mode == 0) zok = (ndz >= 0.0f && ndz < 1.0f);
   else if (P.zclip_mode == 1) zok = (ndz >= -1.0f && ndz < 1.0f);
@@ -220,19 +300,9 @@ project_kernel(const float4 *__restrict__ scene, const __grid_constant__ FramePa
     }
   }
 
-  // ---- colour phase (skipped in stripe renders for Gaussians that cannot touch the stripe)
-  bool vis = visg;
-  const bool need_colour = visg && !(P.stripe_cull && tr.count() == 0u);
-  float col[3] = {0.f, 0.f, 0.f};
-  if (need_colour) {
-    if (P.stripe_cull) {
-#pragma unroll
-      for (int k = 3; k < 9; ++k) {
-        const float4 v = __ldg(&scene[(size_t)(k + 1) * n + ii]);
-        f[4 * k] = v.x; f[4 * k + 1] = v.y; f[4 * k + 2] = v.z; f[4 * k + 3] = v.w;
-      }
-    }
-    // pipelines.rs:99-100 + gaussians.rs:41-99  SH colour along normalize(position - camera.position)
+  // pipelines.rs:99-100 + gaussians.rs:41-99  SH colour along normalize(position - camera.position)
+  float col[3];
+  {
     const float d0 = p0.x - P.cam_pos[0], d1 = p0.y - P.cam_pos[1], d2 = p0.z - P.cam_pos[2];
     const float dn = __fsqrt_rn(d0 * d0 + d1 * d1 + d2 * d2);
     const float x = __fdiv_rn(d0, dn), y = __fdiv_rn(d1, dn), z = __fdiv_rn(d2, dn);
@@ -248,10 +318,9 @@ project_kernel(const float4 *__restrict__ scene, const __grid_constant__ FramePa
       v = v + k4 * sh[12 + c] + k5 * sh[15 + c] + k6 * sh[18 + c] + k7 * sh[21 + c] + k8 * sh[24 + c];
       col[c] = v + 0.5f;
     }
-    vis = finitef(col[0]) && finitef(col[1]) && finitef(col[2]);
-  } else if (P.stripe_cull) {
-    vis = false;
   }
+  // a stripe keeps only what can touch its rows (the others never reach the sort)
+  const bool vis = visg && finitef(col[0]) && finitef(col[1]) && finitef(col[2]) && !(P.stripe_cull && tr.count() == 0u);
   if (!vis) { tr.x0 = 1; tr.x1 = 0; tr.y0 = 1; tr.y1 = 0; }
 
   // power threshold: alpha = min(0.99, op*exp(power)) < 1/255 is certain below pth
@@ -272,39 +341,10 @@ project_kernel(const float4 *__restrict__ scene, const __grid_constant__ FramePa
       r.c = make_float4(col[0], col[1], col[2], pth);
       recs[i] = r;
     }
-    keys[i] = vis ? depth_key(zv) : KEY_CULLED;
-    vals[i] = i;
+    keys[j] = vis ? depth_key(zv) : KEY_CULLED;
+    vals[j] = i;
     rects[i] = make_uint2((uint32_t)tr.x0 | ((uint32_t)tr.y0 << 16), (uint32_t)tr.x1 | ((uint32_t)tr.y1 << 16));
     tcnt[i] = tr.count();   // 4-byte gather target for tile_count_kernel (8 per sector, stays in L2)
-  }
-  if (P.stripe_cull) {
-    const int kept = __syncthreads_count(valid && vis);
-    if (threadIdx.x == 0) block_kept[blockIdx.x] = (uint32_t)kept;
-  }
-}
-
-// Stripe renders: squeeze the (depth key, index) pairs of the Gaussians that survived the stripe
-// cull to the front, in index order (the stable sort's tie-break is the input order).  CTA b owns
-// the 256 pairs project_kernel's CTA b wrote; block_off = exclusive scan of block_kept.
-__global__ void __launch_bounds__(256)
-compact_pairs_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-                     uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
-                     const uint32_t *__restrict__ block_off, uint32_t n) {
-  __shared__ uint32_t wcnt[8];
-  const uint32_t i = blockIdx.x * 256u + threadIdx.x, lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-  uint32_t k = KEY_CULLED, v = 0;
-  if (i < n) { k = keys_in[i]; v = vals_in[i]; }
-  const bool keep = k != KEY_CULLED;
-  const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
-  if (lane == 0) wcnt[w] = __popc(bal);
-  __syncthreads();
-  uint32_t before = 0;
-#pragma unroll
-  for (uint32_t q = 0; q < 8u; ++q) before += (q < w) ? wcnt[q] : 0u;
-  if (keep) {
-    const uint32_t o = block_off[blockIdx.x] + before + __popc(bal & ((1u << lane) - 1u));
-    keys_out[o] = k;
-    vals_out[o] = v;
   }
 }
 

@@ -273,13 +273,14 @@ scan_reduce_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ parti
 }
 
 // single CTA: exclusive scan of the block partials (64-bit running sum for the grand total).
-// With `st` set, the total is the frame's tile-instance count: it is checked against the capacity
-// of the instance buffers ON THE DEVICE (st->n_inst_eff = total if it fits, else 0 and the frame
-// is flagged: every later kernel then has nothing to do and the target stays untouched), which is
-// what lets the host enqueue the rest of the frame without reading the count.
+// With `st` set, the total is a count the next launches were sized for WITHOUT the host having
+// seen it (a stripe's survivors, the frame's tile instances): it is checked against that bound ON
+// THE DEVICE -- *eff_out = total if it fits, else 0 and the frame is flagged (st->overflow): every
+// later kernel then has nothing to do, the target stays untouched, and the host repeats the frame.
 __global__ void __launch_bounds__(1024)
 scan_partials_kernel(uint32_t *__restrict__ partial, uint32_t np, unsigned long long *total_out,
-                     FrameStatus *st = nullptr, unsigned long long cap = 0) {
+                     FrameStatus *st = nullptr, unsigned long long cap = 0, unsigned int *eff_out = nullptr,
+                     bool zero_total_on_overflow = false) {
   __shared__ unsigned long long wsum[32];
   __shared__ unsigned long long carry_s;
   if (threadIdx.x == 0) carry_s = 0;
@@ -305,13 +306,15 @@ scan_partials_kernel(uint32_t *__restrict__ partial, uint32_t np, unsigned long 
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    if (total_out) *total_out = carry_s;
+    unsigned long long total = carry_s;
     if (st) {
-      const bool fits = carry_s <= cap;
-      st->n_inst_eff = fits ? (unsigned int)carry_s : 0u;
-      st->overflow = fits ? 0u : 1u;
-      if (!fits) st->skipped += 1u;
+      const bool already = st->overflow != 0u;      // an earlier stage of this frame did not fit
+      const bool fits = total <= cap && !already;
+      if (eff_out) *eff_out = fits ? (unsigned int)total : 0u;
+      if (!fits && !already) { st->overflow = 1u; st->skipped += 1u; }
+      if (!fits && zero_total_on_overflow) total = 0;
     }
+    if (total_out) *total_out = total;
   }
 }
 

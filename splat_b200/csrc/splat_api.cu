@@ -18,11 +18,13 @@
 #include <new>
 #include <string>
 #include <thread>
+#include <vector>
 
 #include "../../include/splat.h"
 #include "bin.cuh"
 #include "blend.cuh"
 #include "blend_float.cuh"
+#include "comm.cuh"
 #include "common.cuh"
 #include "project.cuh"
 #include "sort.cuh"
@@ -89,7 +91,20 @@ struct splat_ctx {
   uint32_t *last_fb = nullptr;
   cudaStream_t last_stream = nullptr;
   uint32_t retried = 0;
-  uint64_t launches = 0, last_instances = 0, last_visible = 0, last_tiles = 0;
+  uint64_t launches = 0, last_instances = 0, last_visible = 0, last_tiles = 0, last_sort = 0;
+
+  // ---- multi-GPU (comm.cuh).  One process per GPU: this context joined a communicator
+  // (splat_comm_init_rank).  One process, several GPUs: this is a GROUP context
+  // (splat_create_multi) that owns one ordinary context per device in `members`.
+  ncclComm_t comm = nullptr;
+  int n_ranks = 1, rank = 0;
+  bool owns_comm = false;
+  std::vector<splat_ctx *> members;
+  std::vector<uint32_t> bounds;        // group: stripe rows [2 * members], tile aligned
+  uint32_t bounds_geom[2] = {0, 0};    // W, H the bounds were made for
+  uint32_t *d_frame = nullptr;         // member: full W x H frame on its device (gather source / target)
+  size_t frame_cap = 0;
+  uint32_t frames_since_rebalance = 0;
 };
 
 namespace {
@@ -290,6 +305,7 @@ void absorb_status(splat_ctx *c) {
   const FrameStatus &fs = *c->h_status;
   c->last_instances = fs.n_instances;
   c->last_visible = fs.n_visible;
+  c->last_sort = fs.n_sort;
   if (fs.skipped != c->skipped_seen) {          // a frame (or several) wanted more pairs than the buffers hold
     c->frames_skipped += fs.skipped - c->skipped_seen;
     c->skipped_seen = fs.skipped;
@@ -299,6 +315,12 @@ void absorb_status(splat_ctx *c) {
 }
 void poll_status(splat_ctx *c) {
   if (c->status_pending && cudaEventQuery(c->status_ev) == cudaSuccess) absorb_status(c);
+}
+
+// pairs the depth sort of a frame is launched for: all Gaussians, or (stripe frames the host has
+// history for) the same bound the dense projection was launched with
+uint64_t sort_bound_all(const splat_ctx *c, const FrameParams &, bool async, uint32_t n) {
+  return async ? std::min<uint64_t>(n, c->last_sort + c->last_sort / 8 + 65536u) : n;
 }
 
 struct Pass {
@@ -372,7 +394,7 @@ int bin_sort_blend(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cu
     const uint32_t np = std::max(1u, cdiv(n, SC_BLOCK));
     scan_reduce_kernel<<<np, SC_THREADS, 0, s>>>(c->cnt, c->partial, n);
     scan_partials_kernel<<<1, 1024, 0, s>>>(c->partial, np, &c->d_status->n_instances, c->d_status,
-                                            pass.sync_count ? 0xFFFFFFFEull : (unsigned long long)n_bound);
+                                            pass.sync_count ? 0xFFFFFFFEull : (unsigned long long)n_bound, &c->d_status->n_inst_eff);
     scan_apply_kernel<<<np, SC_THREADS, 0, s>>>(c->cnt, c->offs, c->partial, n);
     c->launches += 2;
     LAUNCHED("scan (tile counts)");
@@ -386,6 +408,7 @@ int bin_sort_blend(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cu
     const uint64_t I = c->h_status->n_instances;
     c->last_instances = I;
     c->last_visible = c->h_status->n_visible;
+    c->last_sort = c->h_status->n_sort;
     if (I >= 0xFFFFFFFEull) return fail(c, SPLAT_ERR_UNSUPPORTED, "more than 2^32-2 tile instances in one stripe");
     if (I > c->inst_cap) {
       int rc = ensure_instances(c, I);
@@ -445,37 +468,6 @@ int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cuda
   poll_status(c);
   // Same target geometry as the last frame and its count known: nothing has to block.
   const bool same_geom = c->have_frame && c->geom[0] == P.W && c->geom[1] == P.H && c->geom[2] == P.row0 && c->geom[3] == P.row1;
-  bool async = same_geom && !force_sync && !c->retry_pending && c->cut_frac >= 1024u && !c->cfg.sync_frames;
-  if (async && c->last_instances + c->last_instances / 8 + 65536u > c->inst_cap) {
-    // cudaFree / cudaMalloc wait for the frames in flight; rare (the buffers are grown with 25% headroom)
-    int rc = ensure_instances(c, c->last_instances + c->last_instances / 8 + 65536u);
-    if (rc) return rc;
-  }
-  CU(cudaEventRecord(c->ev[EV_START], s));
-  CU(cudaMemsetAsync(c->d_status, 0, offsetof(FrameStatus, skipped), s));
-  project_kernel<<<cdiv(n, 256), 256, 0, s>>>(c->scene, P, c->recs, c->keys[0], c->vals[0], c->rects, c->tcnt, c->block_kept);
-  LAUNCHED("project_kernel");
-  CU(cudaEventRecord(c->ev[EV_PROJECT], s));
-  int cur = 0;
-  const uint32_t *n_sorted = nullptr;
-  if (P.stripe_cull) {
-    // squeeze out what the stripe cannot see, then sort only the survivors (device-side count)
-    const uint32_t nb = cdiv(n, 256), np = std::max(1u, cdiv(nb, SC_BLOCK));
-    scan_reduce_kernel<<<np, SC_THREADS, 0, s>>>(c->block_kept, c->partial, nb);
-    scan_partials_kernel<<<1, 1024, 0, s>>>(c->partial, np, &c->d_status->n_sort);
-    scan_apply_kernel<<<np, SC_THREADS, 0, s>>>(c->block_kept, c->block_kept, c->partial, nb);
-    compact_pairs_kernel<<<nb, 256, 0, s>>>(c->keys[0], c->vals[0], c->keys[1], c->vals[1], c->block_kept, n);
-    c->launches += 3;
-    LAUNCHED("stripe compaction");
-    cur = 1;
-    n_sorted = reinterpret_cast<const uint32_t *>(&c->d_status->n_sort);   // low word (n < 2^31)
-  }
-  // (a stripe sorts only its survivors -- a device-side count; the CTAs beyond it exit at once)
-  cur = radix_sort(c, s, c->keys, c->vals, n, 32, cur, n_sorted, n);
-  if (cur < 0) return cur;
-  c->order_buf = cur;
-  CU(cudaEventRecord(c->ev[EV_DSORT], s));
-
   // Near cut: the blend reads only the nearest few hundred entries of every tile list (exact early
   // termination), so first bin + sort only the nearest cut_frac/1024 of the Gaussians -- the
   // depth ranks the previous frame makes us expect at the top -- and fall back to the complete
@@ -487,6 +479,46 @@ int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cuda
     const uint64_t keep = (c->last_visible * c->cut_frac + 1023u) / 1024u;
     if (keep < c->last_visible) rank_cut = (uint32_t)(c->last_visible - keep);
   }
+  // near-cut frames read their status on the host (did every pixel converge?); all others need no host wait
+  bool async = same_geom && !force_sync && !c->retry_pending && rank_cut == 0 && !c->cfg.sync_frames;
+  if (async && c->last_instances + c->last_instances / 8 + 65536u > c->inst_cap) {
+    // cudaFree / cudaMalloc wait for the frames in flight; rare (the buffers are grown with 25% headroom)
+    int rc = ensure_instances(c, c->last_instances + c->last_instances / 8 + 65536u);
+    if (rc) return rc;
+  }
+  CU(cudaEventRecord(c->ev[EV_START], s));
+  CU(cudaMemsetAsync(c->d_status, 0, offsetof(FrameStatus, skipped), s));
+  const uint32_t *n_sorted = nullptr;
+  if (!P.stripe_cull) {
+    project_kernel<false><<<cdiv(n, 256), 256, 0, s>>>(c->scene, P, c->recs, c->keys[0], c->vals[0], c->rects, c->tcnt, nullptr, nullptr);
+    LAUNCHED("project_kernel");
+  } else {
+    // Stripe (multi-GPU) frames: a 48 B/Gaussian pre-pass votes which Gaussians can reach the rows
+    // of this stripe; the survivors' indices are compacted in index order and the projection runs
+    // densely over them -- the O(N) work every rank repeats shrinks to the pre-pass.
+    uint32_t *mask = c->cnt, *surv = c->offs;          // both idle until the binning stage
+    const uint32_t nb = cdiv(n, 256), np = std::max(1u, cdiv(nb, SC_BLOCK));
+    // launch bound of the dense projection: the last survivor count the host has seen, +12.5%
+    const uint64_t sort_bound = async ? std::min<uint64_t>(n, c->last_sort + c->last_sort / 8 + 65536u) : n;
+    stripe_cull_kernel<<<nb, 256, 0, s>>>(c->scene, P, mask, c->block_kept);
+    scan_reduce_kernel<<<np, SC_THREADS, 0, s>>>(c->block_kept, c->partial, nb);
+    scan_partials_kernel<<<1, 1024, 0, s>>>(c->partial, np, &c->d_status->n_sort, c->d_status, sort_bound, nullptr, true);
+    scan_apply_kernel<<<np, SC_THREADS, 0, s>>>(c->block_kept, c->block_kept, c->partial, nb);
+    compact_idx_kernel<<<nb, 256, 0, s>>>(mask, c->block_kept, surv, n);
+    n_sorted = reinterpret_cast<const uint32_t *>(&c->d_status->n_sort);   // low word (n < 2^31)
+    project_kernel<true><<<std::max(1u, cdiv(sort_bound, 256)), 256, 0, s>>>(c->scene, P, c->recs, c->keys[0], c->vals[0], c->rects, c->tcnt,
+                                                                          surv, n_sorted);
+    c->launches += 5;
+    LAUNCHED("stripe pre-pass + project_kernel");
+  }
+  CU(cudaEventRecord(c->ev[EV_PROJECT], s));
+  int cur = 0;
+  // (a stripe sorts only its survivors -- a device-side count; the CTAs beyond it exit at once)
+  cur = radix_sort(c, s, c->keys, c->vals, P.stripe_cull ? sort_bound_all(c, P, async, n) : n, 32, cur, n_sorted, n);
+  if (cur < 0) return cur;
+  c->order_buf = cur;
+  CU(cudaEventRecord(c->ev[EV_DSORT], s));
+
   Pass pass;
   pass.rank_cut = rank_cut;
   pass.sync_count = !async;
@@ -559,6 +591,221 @@ int upload_common(splat_ctx *c, uint64_t n) {
   return alloc_scene(c, n);
 }
 
+
+// ---------------------------------------------------------------- multi-GPU: group contexts
+#define NC(expr)                                                                              \
+  do {                                                                                        \
+    ncclResult_t r__ = (expr);                                                                \
+    if (r__ != ncclSuccess) {                                                                 \
+      c->err = std::string(#expr) + ": " + (nccl_api() ? nccl_api()->GetErrorString(r__) : "NCCL"); \
+      return SPLAT_ERR_CUDA;                                                                  \
+    }                                                                                         \
+  } while (0)
+
+// equal numbers of tile rows (remainder to the first members)
+void equal_bounds(std::vector<uint32_t> &b, uint32_t H, int parts) {
+  const uint32_t tr = cdiv(H, TILE);
+  b.assign((size_t)2 * parts, 0u);
+  uint32_t r = 0;
+  for (int k = 0; k < parts; ++k) {
+    const uint32_t rows = tr / parts + ((uint32_t)k < tr % parts ? 1u : 0u);
+    b[2 * k] = std::min(r * TILE, H);
+    r += rows;
+    b[2 * k + 1] = std::min(r * TILE, H);
+  }
+}
+
+// New stripe boundaries from the members' measured frame times: the cost of a tile row is taken as
+// uniform inside the stripe that rendered it, and the rows are re-cut so that the heaviest stripe is
+// as light as possible (greedy fill against a bisected bottleneck).  SURVEY H6.
+void rebalance_bounds(std::vector<uint32_t> &b, const std::vector<float> &ms, uint32_t H) {
+  const int parts = (int)ms.size();
+  const uint32_t tr = cdiv(H, TILE);
+  std::vector<double> w(tr, 0.0);
+  for (int k = 0; k < parts; ++k) {
+    const uint32_t t0 = b[2 * k] / TILE, t1 = cdiv(b[2 * k + 1], TILE);
+    for (uint32_t t = t0; t < t1 && t < tr; ++t) w[t] = std::max(1e-4, (double)ms[k]) / std::max(1u, t1 - t0);
+  }
+  double lo = 0.0, hi = 0.0;
+  for (double v : w) { lo = std::max(lo, v); hi += v; }
+  auto cuts_for = [&](double cap, std::vector<uint32_t> *out) {
+    uint32_t t = 0;
+    if (out) out->assign((size_t)2 * parts, 0u);
+    for (int k = 0; k < parts; ++k) {
+      const uint32_t start = t;
+      double acc = 0.0;
+      while (t < tr && acc + w[t] <= cap) acc += w[t++];
+      if (out) { (*out)[2 * k] = std::min(start * TILE, H); (*out)[2 * k + 1] = std::min(t * TILE, H); }
+    }
+    return t >= tr;
+  };
+  for (int it = 0; it < 50; ++it) {
+    const double mid = 0.5 * (lo + hi);
+    if (cuts_for(mid, nullptr)) hi = mid; else lo = mid;
+  }
+  std::vector<uint32_t> nb;
+  if (cuts_for(hi * (1.0 + 1e-9) + 1e-12, &nb)) { nb[(size_t)2 * parts - 1] = H; b = nb; }
+}
+
+int ensure_frame(splat_ctx *m, size_t px) {
+  splat_ctx *c = m;
+  if (px <= m->frame_cap) return SPLAT_OK;
+  CU(cudaDeviceSynchronize());
+  dev_free(m->d_frame);
+  CU(dev_alloc(&m->d_frame, px));
+  m->frame_cap = px;
+  return SPLAT_OK;
+}
+
+// C0 for a group: member 0 holds the packed device scene; the others receive it (ncclBroadcast).
+int group_broadcast_scene(splat_ctx *g) {
+  splat_ctx *c = g;
+  NcclApi *N = nccl_api();
+  if (!N) return fail(g, SPLAT_ERR_UNSUPPORTED, "NCCL is not available");
+  splat_ctx *root = g->members[0];
+  const uint64_t n = root->n;
+  for (size_t i = 1; i < g->members.size(); ++i) {
+    splat_ctx *m = g->members[i];
+    CU(cudaSetDevice(m->cfg.device));
+    int rc = alloc_scene(m, n);
+    if (rc) { g->err = m->err; return rc; }
+  }
+  NC(N->GroupStart());
+  for (splat_ctx *m : g->members) {
+    CU(cudaSetDevice(m->cfg.device));
+    NC(N->Broadcast(root->scene, m->scene, (size_t)SCENE_PLANES * n * 4u, ncclFloat, 0, m->comm, m->stream));
+  }
+  NC(N->GroupEnd());
+  for (splat_ctx *m : g->members) {
+    CU(cudaSetDevice(m->cfg.device));
+    CU(cudaStreamSynchronize(m->stream));
+  }
+  g->n = (uint32_t)n;
+  return SPLAT_OK;
+}
+
+// One frame on every member: each renders its stripe of rows into its own W x H device frame, the
+// stripes are gathered into member 0's frame with one grouped send/recv, member 0 returns the frame.
+// clear_value < 0: fb_inout is blended onto (each member uploads its own rows); else cleared on the device.
+int group_render(splat_ctx *g, const splat_camera *cam, uint32_t *fb, uint32_t W, uint32_t H, long long clear_value) {
+  splat_ctx *c = g;
+  NcclApi *N = nccl_api();
+  if (!N) return fail(g, SPLAT_ERR_UNSUPPORTED, "NCCL is not available");
+  const int G = (int)g->members.size();
+  if (!g->n) return fail(g, SPLAT_ERR_STATE, "no scene uploaded");
+  if (!fb) return fail(g, SPLAT_ERR_INVALID, "framebuffer is null");
+  if (g->bounds.size() != (size_t)2 * G || g->bounds_geom[0] != W || g->bounds_geom[1] != H) {
+    equal_bounds(g->bounds, H, G);
+    g->bounds_geom[0] = W; g->bounds_geom[1] = H;
+    g->frames_since_rebalance = 0;
+  }
+  const size_t px = (size_t)W * H;
+  std::vector<char> todo((size_t)G, 1);     // members whose stripe still has to be rendered
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    // enqueue: upload / clear (first attempt only: a skipped stripe left its rows untouched), kernels
+    for (int k = 0; k < G; ++k) {
+      splat_ctx *m = g->members[k];
+      const uint32_t r0 = g->bounds[2 * k], r1 = g->bounds[2 * k + 1];
+      CU(cudaSetDevice(m->cfg.device));
+      int rc = ensure_frame(m, px);
+      if (rc) { g->err = m->err; return rc; }
+      if (r1 <= r0 || !todo[k]) continue;
+      FrameParams P;
+      rc = make_params(m, cam, W, H, r0, r1, &P);
+      if (rc) { g->err = m->err; return rc; }
+      uint32_t *rows = m->d_frame + (size_t)r0 * W;
+      const size_t bytes = (size_t)(r1 - r0) * W * 4u;
+      cudaEvent_t wait_ev = nullptr;
+      CU(cudaEventRecord(m->ev[EV_H2D0], m->copy_stream));
+      if (attempt > 0) {
+        // rows are still as uploaded / cleared
+      } else if (clear_value < 0) {
+        CU(cudaMemcpyAsync(rows, fb + (size_t)r0 * W, bytes, cudaMemcpyHostToDevice, m->copy_stream));
+      } else if (clear_value == 0 || (((uint32_t)clear_value & 0xFFu) * 0x01010101u) == (uint32_t)clear_value) {
+        CU(cudaMemsetAsync(rows, (int)((uint32_t)clear_value & 0xFFu), bytes, m->copy_stream));
+      } else {
+        fill_u32_kernel<<<cdiv(bytes / 4u, 1024), 256, 0, m->copy_stream>>>(rows, (uint32_t)clear_value, bytes / 4u);
+      }
+      CU(cudaEventRecord(m->ev[EV_H2D1], m->copy_stream));
+      CU(cudaEventRecord(m->h2d_done, m->copy_stream));
+      wait_ev = m->h2d_done;
+      rc = render_frame(m, P, rows, m->stream, wait_ev, attempt > 0);
+      if (rc) { g->err = m->err; return rc; }
+    }
+    // C1: one grouped gather, enqueued on every member's stream right behind its blend kernel
+    NC(N->GroupStart());
+    for (int k = 0; k < G; ++k) {
+      splat_ctx *m = g->members[k];
+      CU(cudaSetDevice(m->cfg.device));
+      NC(gather_stripes(N, m->comm, G, k, 0, m->d_frame, W, g->bounds.data(), m->stream));
+    }
+    NC(N->GroupEnd());
+    splat_ctx *root = g->members[0];
+    CU(cudaSetDevice(root->cfg.device));
+    CU(cudaEventRecord(root->ev[EV_D2H0], root->stream));
+    CU(cudaMemcpyAsync(fb, root->d_frame, px * 4u, cudaMemcpyDeviceToHost, root->stream));
+    CU(cudaEventRecord(root->ev[EV_D2H1], root->stream));
+    bool again = false;
+    for (int k = 0; k < G; ++k) {
+      splat_ctx *m = g->members[k];
+      if (g->bounds[2 * k + 1] <= g->bounds[2 * k] && k != 0) continue;
+      CU(cudaSetDevice(m->cfg.device));
+      int rc = wait_done(m, nullptr, m->stream, "frame (group member)");
+      if (rc) { g->err = m->err; return rc; }
+      if (m->status_pending) absorb_status(m);
+      todo[k] = 0;
+      if (m->retry_pending) {          // this member's stripe was skipped on the device: grow, render it again
+        m->retry_pending = false;
+        rc = ensure_instances(m, m->last_instances + m->last_instances / 4 + 65536u);
+        if (rc) { g->err = m->err; return rc; }
+        todo[k] = 1;
+        again = true;
+      }
+    }
+    root->host_copy = true;
+    if (!again) break;
+  }
+  g->have_frame = true;
+  // re-cut the stripes from the measured times when they drift apart (at most every 8th frame: a
+  // new cut costs each member one frame with a host round trip)
+  g->frames_since_rebalance += 1;
+  if (G > 1 && g->cfg.reserved == 0 && (g->frames_since_rebalance == 2 || g->frames_since_rebalance % 8 == 0)) {
+    std::vector<float> ms((size_t)G, 0.f);
+    float mx = 0.f, mn = 1e30f;
+    for (int k = 0; k < G; ++k) {
+      splat_ctx *m = g->members[k];
+      if (g->bounds[2 * k + 1] <= g->bounds[2 * k]) { ms[k] = 0.f; mn = 0.f; continue; }
+      CU(cudaSetDevice(m->cfg.device));
+      float v = 0.f;
+      cudaEventElapsedTime(&v, m->ev[EV_START], m->ev[EV_BLEND]);
+      ms[k] = v; mx = std::max(mx, v); mn = std::min(mn, v);
+    }
+    if (mx > 1.15f * mn + 0.02f) rebalance_bounds(g->bounds, ms, H);
+  }
+  return SPLAT_OK;
+}
+
+int group_timings(splat_ctx *g, splat_timings *t) {
+  std::memset(t, 0, sizeof(*t));
+  for (size_t k = 0; k < g->members.size(); ++k) {
+    splat_ctx *m = g->members[k];
+    if (!m->have_frame) continue;
+    splat_timings tm;
+    int rc = splat_get_timings(m, &tm);
+    if (rc) { g->err = m->err; return rc; }
+    t->project_ms = std::max(t->project_ms, tm.project_ms); t->sort_ms = std::max(t->sort_ms, tm.sort_ms);
+    t->bin_ms = std::max(t->bin_ms, tm.bin_ms); t->blend_ms = std::max(t->blend_ms, tm.blend_ms);
+    t->total_ms = std::max(t->total_ms, tm.total_ms);
+    t->h2d_ms = std::max(t->h2d_ms, tm.h2d_ms);
+    if (k == 0) t->d2h_ms = tm.d2h_ms;
+    t->frames_retried += tm.frames_retried; t->frames_skipped += tm.frames_skipped;
+    t->n_visible += tm.n_visible; t->n_instances += tm.n_instances; t->n_tiles += tm.n_tiles;
+    t->kernel_launches += tm.kernel_launches;
+  }
+  t->n_gaussians = g->n;
+  return SPLAT_OK;
+}
+
 }  // namespace
 
 thread_local char g_create_error[256] = "";
@@ -577,7 +824,7 @@ void splat_config_default(splat_config *cfg) {
   cfg->tile = TILE;
   cfg->max_instances = 0;
   cfg->blend_mode = SPLAT_BLEND_REFERENCE;
-  cfg->near_cut = 0;
+  cfg->near_cut = -1;         // automatic (exact either way; 0 switches it off)
   cfg->sync_frames = 0;
   cfg->reserved = 0;
 }
@@ -602,9 +849,10 @@ int splat_create(splat_ctx **out, const splat_config *cfg) {
   if (c->cfg.blend_mode != SPLAT_BLEND_REFERENCE && c->cfg.blend_mode != SPLAT_BLEND_FLOAT)
     return bail_msg(SPLAT_ERR_UNSUPPORTED, "blend_mode must be SPLAT_BLEND_REFERENCE or SPLAT_BLEND_FLOAT");
   if (c->cfg.near_cut < -1 || c->cfg.near_cut > 1024) return bail_msg(SPLAT_ERR_INVALID, "near_cut must be -1, 0 or 1..1024");
-  if (c->cfg.near_cut != 0 && c->cfg.blend_mode != SPLAT_BLEND_REFERENCE)
+  if (c->cfg.near_cut > 0 && c->cfg.blend_mode != SPLAT_BLEND_REFERENCE)
     return bail_msg(SPLAT_ERR_UNSUPPORTED, "the near cut belongs to the reference blend (the float blend terminates early by itself)");
-  // 0 = off (default: see DESIGN.md, known issue), -1 = automatic, 1..1024 = fixed fraction
+  if (c->cfg.blend_mode != SPLAT_BLEND_REFERENCE) c->cfg.near_cut = 0;   // "automatic" means none there
+  // 0 = off, -1 = automatic (default), 1..1024 = fixed fraction
   c->cut_frac = c->cfg.near_cut == 0 ? 1024u : (c->cfg.near_cut < 0 ? NEAR_CUT_DEFAULT : (uint32_t)c->cfg.near_cut);
   if (!(c->cfg.lowpass >= 0.0f) || !std::isfinite(c->cfg.sample_offset)) return bail_msg(SPLAT_ERR_INVALID, "lowpass must be >= 0 and sample_offset finite");
   if (cudaSetDevice(c->cfg.device) != cudaSuccess) return bail(SPLAT_ERR_CUDA);
@@ -637,7 +885,18 @@ int splat_create(splat_ctx **out, const splat_config *cfg) {
 
 void splat_destroy(splat_ctx *c) {
   if (!c) return;
+  if (!c->members.empty()) {           // group context: it owns nothing on a device itself
+    for (splat_ctx *m : c->members) splat_destroy(m);
+    delete c;
+    return;
+  }
   cudaSetDevice(c->cfg.device);
+  if (c->comm && c->owns_comm) {
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (NcclApi *N = nccl_api()) N->CommDestroy(c->comm);
+    c->comm = nullptr;
+  }
+  dev_free(c->d_frame);
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_scene(c);
   dev_free(c->hist); dev_free(c->tot); dev_free(c->partial); dev_free(c->ranges); dev_free(c->units); dev_free(c->far_cnt); dev_free(c->far_diff); dev_free(c->tile_failed); dev_free(c->n_units); dev_free(c->d_status); dev_free(c->d_fb); dev_free(c->d_tap);
@@ -657,6 +916,11 @@ const char *splat_last_error(const splat_ctx *c) { return c ? c->err.c_str() : "
 int splat_upload_soa(splat_ctx *c, const float *pos4, const float *scale3, const float *opacity,
                      const float *rot_xyzw, const float *sh48, uint64_t n) {
   if (!c) return SPLAT_ERR_INVALID;
+  if (!c->members.empty()) {
+    int rc = splat_upload_soa(c->members[0], pos4, scale3, opacity, rot_xyzw, sh48, n);
+    if (rc) { c->err = c->members[0]->err; return rc; }
+    return group_broadcast_scene(c);
+  }
   if (!pos4 || !scale3 || !opacity || !rot_xyzw || !sh48) return fail(c, SPLAT_ERR_INVALID, "null scene array");
   int rc = upload_common(c, n);
   if (rc) return rc;
@@ -682,6 +946,11 @@ int splat_upload_soa(splat_ctx *c, const float *pos4, const float *scale3, const
 
 int splat_upload_aos(splat_ctx *c, const float *g59, uint64_t n) {
   if (!c) return SPLAT_ERR_INVALID;
+  if (!c->members.empty()) {
+    int rc = splat_upload_aos(c->members[0], g59, n);
+    if (rc) { c->err = c->members[0]->err; return rc; }
+    return group_broadcast_scene(c);
+  }
   if (!g59) return fail(c, SPLAT_ERR_INVALID, "null scene array");
   int rc = upload_common(c, n);
   if (rc) return rc;
@@ -713,6 +982,7 @@ static int report_skipped(splat_ctx *c) {
 int splat_render_device(splat_ctx *c, const splat_camera *cam, void *fb_rows_dev, uint32_t W, uint32_t H,
                         uint32_t row0, uint32_t row1, void *stream) {
   if (!c) return SPLAT_ERR_INVALID;
+  if (!c->members.empty()) return fail(c, SPLAT_ERR_UNSUPPORTED, "a group context renders through the host-buffer entry points");
   if (!c->n) return fail(c, SPLAT_ERR_STATE, "no scene uploaded");
   if (!fb_rows_dev) return fail(c, SPLAT_ERR_INVALID, "framebuffer is null");
   FrameParams P;
@@ -747,6 +1017,10 @@ static int host_frame(splat_ctx *c, const FrameParams &P, uint32_t *host_fb, siz
 int splat_render_rows(splat_ctx *c, const splat_camera *cam, uint32_t *fb_rows, uint32_t W, uint32_t H,
                       uint32_t row0, uint32_t row1) {
   if (!c) return SPLAT_ERR_INVALID;
+  if (!c->members.empty()) {
+    if (row0 != 0 || row1 != H) return fail(c, SPLAT_ERR_UNSUPPORTED, "a group context renders whole frames (it cuts the stripes itself)");
+    return group_render(c, cam, fb_rows, W, H, -1);
+  }
   if (!c->n) return fail(c, SPLAT_ERR_STATE, "no scene uploaded");
   if (!fb_rows) return fail(c, SPLAT_ERR_INVALID, "framebuffer is null");
   FrameParams P;
@@ -777,6 +1051,7 @@ int splat_render(splat_ctx *c, const splat_camera *cam, uint32_t *fb, uint32_t W
 int splat_render_cleared(splat_ctx *c, const splat_camera *cam, uint32_t *fb_out, uint32_t W, uint32_t H,
                          uint32_t clear) {
   if (!c) return SPLAT_ERR_INVALID;
+  if (!c->members.empty()) return group_render(c, cam, fb_out, W, H, (long long)clear);
   if (!c->n) return fail(c, SPLAT_ERR_STATE, "no scene uploaded");
   if (!fb_out) return fail(c, SPLAT_ERR_INVALID, "framebuffer is null");
   FrameParams P;
@@ -824,6 +1099,10 @@ int splat_debug_render_float(splat_ctx *c, const splat_camera *cam, uint32_t *fb
 
 int splat_get_timings(splat_ctx *c, splat_timings *t) {
   if (!c || !t) return SPLAT_ERR_INVALID;
+  if (!c->members.empty()) {
+    if (!c->have_frame) return fail(c, SPLAT_ERR_STATE, "no frame rendered yet");
+    return group_timings(c, t);
+  }
   if (!c->have_frame) return fail(c, SPLAT_ERR_STATE, "no frame rendered yet");
   CU(cudaSetDevice(c->cfg.device));
   if (c->status_pending) {
@@ -862,6 +1141,7 @@ int splat_get_timings(splat_ctx *c, splat_timings *t) {
 
 int splat_get_tile_loads(splat_ctx *c, uint32_t *per_tile, uint64_t cap, uint64_t *n_tiles) {
   if (!c || !per_tile || !n_tiles) return SPLAT_ERR_INVALID;
+  if (!c->members.empty()) return fail(c, SPLAT_ERR_UNSUPPORTED, "ask the member that rendered the stripe");
   if (!c->have_frame) return fail(c, SPLAT_ERR_STATE, "no frame rendered yet");
   if (!c->loads_valid) return fail(c, SPLAT_ERR_STATE, "the last frame's second pass binned only part of the screen (near cut): no complete tile lists");
   CU(cudaSetDevice(c->cfg.device));
@@ -888,7 +1168,7 @@ int splat_debug_project(splat_ctx *c, const splat_camera *cam, uint32_t W, uint3
   if (rc) return rc;
   CU(cudaSetDevice(c->cfg.device));
   CU(cudaMemsetAsync(c->recs, 0, (size_t)c->n * sizeof(Rec), c->stream));
-  project_kernel<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->scene, P, c->recs, c->keys[0], c->vals[0], c->rects, c->tcnt, c->block_kept);
+  project_kernel<false><<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->scene, P, c->recs, c->keys[0], c->vals[0], c->rects, c->tcnt, nullptr, nullptr);
   CU(cudaGetLastError());
   if (records12) CU(cudaMemcpyAsync(records12, c->recs, (size_t)c->n * sizeof(Rec), cudaMemcpyDeviceToHost, c->stream));
   if (depth_keys) CU(cudaMemcpyAsync(depth_keys, c->keys[0], (size_t)c->n * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -952,6 +1232,121 @@ int splat_debug_blend_stats(splat_ctx *c, uint64_t *out8, int reset) {
   (void)reset;
   return fail(c, SPLAT_ERR_UNSUPPORTED, "library built without -DSPLAT_STATS");
 #endif
+}
+
+int splat_create_multi(splat_ctx **out, const splat_config *cfg, const int32_t *devices, int32_t n_devices) {
+  if (!out) return SPLAT_ERR_INVALID;
+  *out = nullptr;
+  g_create_error[0] = 0;
+  if (!devices || n_devices < 1 || n_devices > 64) {
+    std::snprintf(g_create_error, sizeof g_create_error, "devices must list 1..64 CUDA device ordinals");
+    return SPLAT_ERR_INVALID;
+  }
+  NcclApi *N = nccl_api();
+  if (!N) {
+    std::snprintf(g_create_error, sizeof g_create_error, "NCCL is not available: %s", NcclApi().error.c_str());
+    return SPLAT_ERR_UNSUPPORTED;
+  }
+  splat_ctx *g = new (std::nothrow) splat_ctx();
+  if (!g) return SPLAT_ERR_NOMEM;
+  if (cfg) g->cfg = *cfg; else splat_config_default(&g->cfg);
+  g->cfg.device = devices[0];
+  for (int k = 0; k < n_devices; ++k) {
+    splat_config mc = g->cfg;
+    mc.device = devices[k];
+    mc.near_cut = 0;                 // stripes use the no-round-trip path
+    splat_ctx *m = nullptr;
+    const int rc = splat_create(&m, &mc);
+    if (rc) { splat_destroy(g); return rc; }
+    g->members.push_back(m);
+  }
+  std::vector<ncclComm_t> comms((size_t)n_devices, nullptr);
+  std::vector<int> devs(devices, devices + n_devices);
+  const ncclResult_t r = N->CommInitAll(comms.data(), n_devices, devs.data());
+  if (r != ncclSuccess) {
+    std::snprintf(g_create_error, sizeof g_create_error, "ncclCommInitAll: %s", N->GetErrorString(r));
+    splat_destroy(g);
+    return SPLAT_ERR_CUDA;
+  }
+  for (int k = 0; k < n_devices; ++k) {
+    g->members[k]->comm = comms[k];
+    g->members[k]->owns_comm = true;
+    g->members[k]->n_ranks = n_devices;
+    g->members[k]->rank = k;
+  }
+  g->n_ranks = n_devices;
+  *out = g;
+  return SPLAT_OK;
+}
+
+int splat_comm_unique_id(void *id128) {
+  if (!id128) return SPLAT_ERR_INVALID;
+  NcclApi *N = nccl_api();
+  if (!N) return SPLAT_ERR_UNSUPPORTED;
+  static_assert(sizeof(ncclUniqueId) == SPLAT_UNIQUE_ID_BYTES, "ncclUniqueId is 128 bytes");
+  return N->GetUniqueId(static_cast<ncclUniqueId *>(id128)) == ncclSuccess ? SPLAT_OK : SPLAT_ERR_CUDA;
+}
+
+int splat_comm_init_rank(splat_ctx *c, const void *id128, int32_t n_ranks, int32_t rank) {
+  if (!c || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return SPLAT_ERR_INVALID;
+  if (!c->members.empty()) return fail(c, SPLAT_ERR_STATE, "a group context owns its communicators already");
+  if (c->comm) return fail(c, SPLAT_ERR_STATE, "the context already joined a communicator");
+  NcclApi *N = nccl_api();
+  if (!N) return fail(c, SPLAT_ERR_UNSUPPORTED, "NCCL is not available");
+  CU(cudaSetDevice(c->cfg.device));
+  ncclUniqueId id;
+  std::memcpy(&id, id128, sizeof id);
+  NC(N->CommInitRank(&c->comm, n_ranks, id, rank));
+  c->owns_comm = true;
+  c->n_ranks = n_ranks;
+  c->rank = rank;
+  return SPLAT_OK;
+}
+
+int splat_comm_broadcast_scene(splat_ctx *c, int32_t root, uint64_t n) {
+  if (!c || !c->comm) return c ? fail(c, SPLAT_ERR_STATE, "no communicator") : SPLAT_ERR_INVALID;
+  if (root < 0 || root >= c->n_ranks) return fail(c, SPLAT_ERR_INVALID, "bad root");
+  NcclApi *N = nccl_api();
+  CU(cudaSetDevice(c->cfg.device));
+  if (c->rank == root) {
+    if (!c->n || c->n != n) return fail(c, SPLAT_ERR_STATE, "root: upload the scene first (n must be its size)");
+  } else {
+    int rc = alloc_scene(c, n);
+    if (rc) return rc;
+  }
+  NC(N->Broadcast(c->scene, c->scene, (size_t)SCENE_PLANES * n * 4u, ncclFloat, root, c->comm, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return SPLAT_OK;
+}
+
+int splat_gather_stripes(splat_ctx *c, void *fb_dev, uint32_t W, uint32_t H, const uint32_t *bounds, int32_t root, void *stream) {
+  if (!c || !fb_dev || !bounds) return SPLAT_ERR_INVALID;
+  if (c->n_ranks <= 1) return SPLAT_OK;
+  if (!c->comm) return fail(c, SPLAT_ERR_STATE, "no communicator");
+  if (root < 0 || root >= c->n_ranks) return fail(c, SPLAT_ERR_INVALID, "bad root");
+  uint32_t prev = 0;
+  for (int r = 0; r < c->n_ranks; ++r) {
+    if (bounds[2 * r] != prev || bounds[2 * r + 1] < bounds[2 * r]) return fail(c, SPLAT_ERR_INVALID, "stripes must be contiguous and ordered");
+    prev = bounds[2 * r + 1];
+  }
+  if (prev != H) return fail(c, SPLAT_ERR_INVALID, "stripes must cover the image");
+  NcclApi *N = nccl_api();
+  CU(cudaSetDevice(c->cfg.device));
+  NC(gather_stripes(N, c->comm, c->n_ranks, c->rank, root, static_cast<uint32_t *>(fb_dev), W, bounds,
+                    stream ? static_cast<cudaStream_t>(stream) : c->stream));
+  return SPLAT_OK;
+}
+
+int splat_group_get_bounds(splat_ctx *c, uint32_t *bounds, int32_t cap_ranks, int32_t *n_ranks) {
+  if (!c || !n_ranks) return SPLAT_ERR_INVALID;
+  *n_ranks = (int32_t)c->members.size();
+  if (c->members.empty()) return fail(c, SPLAT_ERR_STATE, "not a group context");
+  if (bounds)
+    for (int k = 0; k < *n_ranks && k < cap_ranks && (size_t)(2 * k + 1) < c->bounds.size(); ++k) {
+      bounds[2 * k] = c->bounds[2 * k];
+      bounds[2 * k + 1] = c->bounds[2 * k + 1];
+    }
+  return SPLAT_OK;
 }
 
 int splat_pin_host(void *p, uint64_t bytes) {

@@ -112,5 +112,5 @@ def test_float_and_reference_blends_differ_only_by_the_truncation_bias(lib, orc)
 
 def test_float_mode_rejects_the_near_cut(lib):
     with pytest.raises(lib.SplatError) as e:
-        lib.Context(device=0, blend_mode=lib.SPLAT_BLEND_FLOAT, near_cut=-1)
+        lib.Context(device=0, blend_mode=lib.SPLAT_BLEND_FLOAT, near_cut=128)
     assert e.value.code == -4 and "near cut" in str(e.value)

@@ -237,15 +237,9 @@ def test_deep_lists_exact_early_termination(lib, orc, case):
     assert np.array_equal(fb, ref), f"{np.count_nonzero(fb != ref)} of {W*H} pixels differ"
 
 
-# The near cut is experimental and off by default; its automatic mode did not return on two
-# mid-size scenes in the last GPU run of round 1 (known issue).  These tests passed on
-# the B200 (profiles/r1v_*: 28 passed) but only run on request, so that an unattended test run can
-# never sit in that path:  SPLAT_TEST_NEAR_CUT=1 python -m pytest tests -m gpu -k near_cut
-_NEAR_CUT = pytest.mark.skipif(os.environ.get("SPLAT_TEST_NEAR_CUT") != "1",
-                               reason="experimental near cut: set SPLAT_TEST_NEAR_CUT=1 (DESIGN.md, known issue)")
-
-
-@_NEAR_CUT
+# The near cut (bin + sort only the nearest Gaussians first, exact by construction).  Round 1 gated
+# these tests because the automatic mode dead-locked on two mid-size scenes; the cause (mbarriers
+# invalidated and re-initialised between suffix attempts) is fixed -- profiles/r2_near_cut_hang.txt.
 @pytest.mark.parametrize("frac,expect_fallback", [(512, False), (128, None), (16, None), (1, True)])
 def test_near_cut_is_exact(lib, orc, frac, expect_fallback):
     """Near cut: the second and later frames of a context first bin + sort only the nearest
@@ -278,7 +272,6 @@ def test_near_cut_is_exact(lib, orc, frac, expect_fallback):
     ctx.close()
 
 
-@_NEAR_CUT
 def test_near_cut_stripes_and_empty_regions(lib, orc):
     """Near cut with a stripe render and with screen regions nothing covers (tiles whose list is
     empty both before and after the cut must not trigger the fall-back, tiles whose list the cut
