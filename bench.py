@@ -205,15 +205,17 @@ def run_reference(args):
 
 def workload_config(args):
     """identical for both arms and every N (the driver compares it)"""
-    return {"workload": f"C3 bicycle-sized synthetic scene: {args.n} Gaussians (seed 0x{SEED:X}), "
+    name = "C4 garden-sized" if args.width >= 3840 else ("C3 bicycle-sized" if args.n >= 3_000_000 else "C5 sweep point")
+    return {"workload": f"{name} synthetic scene: {args.n} Gaussians (seed 0x{SEED:X}), "
                         f"{args.width}x{args.height}, camera (0,0,5) orbiting 10 deg yaw/frame, Pipeline02 (low-pass 0.3)",
             "n_gaussians": args.n, "width": args.width, "height": args.height,
             "l2_policy": "inputs larger than L2 (scene 160 B x N, per-frame buffers > 126 MB); no explicit flush"}
 
 
 def parallelism(args, world):
-    return (f"screen-tile stripes x{world}, " + ("equal" if args.equal_stripes else "balanced from a probe frame")
-            + ", scene replicated, one NCCL send/recv gather per frame") if world > 1 else "single GPU"
+    return (f"screen-tile stripes x{world}, " + ("equal" if args.equal_stripes else "cut from a probe frame, re-cut from measured per-rank times")
+            + ", scene broadcast once (splat_comm_broadcast_scene), one grouped ncclSend/ncclRecv gather per frame "
+              "(splat_gather_stripes)") if world > 1 else "single GPU"
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -243,14 +245,23 @@ def run_ours(args):
     W, H, n = args.width, args.height, args.n
     K, Wm = args.steps, args.warmup
 
-    # ---- scene: generated on rank 0, broadcast once over NCCL (C0), uploaded on every rank
+    # ---- scene: generated and uploaded on rank 0, then broadcast once inside the library (C0:
+    # ncclBroadcast of the packed device scene over the context's own communicator)
     from splat_b200 import stripes
-    sc = stripes.broadcast_scene(make_scene(n) if rank == 0 else None, rank, dev)
-    torch.cuda.empty_cache()
-    ctx = _lib.Context(device=local, lowpass=LOWPASS, near_cut=args.near_cut if world == 1 else 0)   # stripes: no host waits
+    ctx = _lib.Context(device=local, lowpass=LOWPASS, near_cut=args.near_cut)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(ctx.unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)                       # launcher plumbing: carries the 128-byte id
+        ctx.comm_init(bytes(uid.cpu().numpy().tobytes()), world, rank)
+    sc = make_scene(n) if rank == 0 else None
     t0 = time.time()
-    ctx.upload(sc)
-    log(f"[bench] rank {rank}: scene uploaded in {time.time() - t0:.1f}s")
+    if rank == 0:
+        ctx.upload(sc)
+    if world > 1:
+        ctx.broadcast_scene(0, n)
+    log(f"[bench] rank {rank}: scene ready in {time.time() - t0:.1f}s")
 
     cams_all = orbit_cameras(W, H, 2 * (Wm + K))
     cam_structs = [_lib.camera_struct(_CamView(c)) for c in cams_all]
@@ -283,8 +294,10 @@ def run_ours(args):
     log(f"[bench] rank {rank}: rows [{r0},{r1})")
 
     def gather_frame():
-        """C1: stripes -> rank 0's full frame, straight from/into the render target (no staging)."""
-        stripes.gather_stripes(fb_dev, bounds, rank)
+        """C1: stripes -> rank 0's full frame, straight from/into the render target (no staging):
+        splat_gather_stripes, grouped ncclSend/ncclRecv on the render stream."""
+        if world > 1:
+            ctx.gather_stripes(fb_dev.data_ptr(), W, H, bounds, 0, stream.cuda_stream)
 
     repeats = [0]
 
@@ -294,16 +307,22 @@ def run_ours(args):
 
     def frame_device(i):
         if r1 > r0:
-            try:
-                render_stripe(i)
-            except _lib.SplatError as e:
-                # SPLAT_ERR_RETRY: the previous frame's tile instances outgrew the launch bound (+12.5% per
-                # frame) and it was skipped on the device; render it again, then this one (both are timed)
-                if e.code != -6:
-                    raise
-                repeats[0] += 1
-                render_stripe(max(i - 1, 0))
-                render_stripe(i)
+            for attempt in range(4):
+                try:
+                    render_stripe(i)
+                    break
+                except _lib.SplatError as e:
+                    # SPLAT_ERR_RETRY: the previous frame's tile instances outgrew the launch bound (+12.5% per
+                    # frame) and it was abandoned on the device; the library has grown its buffers.  Render that
+                    # frame again, then this one (all of it inside the timed region).
+                    if e.code != -6 or attempt == 3:
+                        raise
+                    repeats[0] += 1
+                    try:
+                        render_stripe(max(i - 1, 0))
+                    except _lib.SplatError as e2:
+                        if e2.code != -6:
+                            raise
         gather_frame()
 
     def sync_all():
@@ -311,6 +330,28 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    # ---- refine the stripes from MEASURED per-rank frame times (untimed, before the warm-up)
+    if world > 1 and not args.equal_stripes:
+        for it in range(args.rebalance_rounds):
+            tsum = 0.0
+            for i in range(4):
+                frame_device(i)
+                if r1 > r0 and i >= 1:
+                    tsum += ctx.timings()["total_ms"]
+            sync_all()
+            tt = torch.tensor([tsum / 3.0], device=dev, dtype=torch.float64)
+            allt = [torch.zeros_like(tt) for _ in range(world)]
+            dist.all_gather(allt, tt)
+            times = [float(x.item()) for x in allt]
+            new_bounds = stripes.rebalance(bounds, times, H)
+            if rank == 0:
+                log(f"[bench] rebalance {it}: per-rank ms " + " ".join(f"{t:.3f}" for t in times) + f" -> {new_bounds}")
+            if new_bounds == bounds or max(times) < 1.08 * min(t for t in times if t > 0):
+                break
+            bounds = new_bounds
+            stripes.check_bounds(bounds, H)
+            r0, r1 = bounds[rank]
 
     # ---- value: device-resident frames
     for i in range(Wm):
@@ -320,7 +361,8 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage = {"project_ms": 0.0, "sort_ms": 0.0, "bin_ms": 0.0, "blend_ms": 0.0, "total_ms": 0.0}
+    stage = {"project_ms": 0.0, "sort_ms": 0.0, "bin_ms": 0.0, "blend_ms": 0.0, "second_pass_ms": 0.0, "total_ms": 0.0}
+    second_sum = 0
     inst_sum, launches, cut_sum, fallbacks = 0, 0, 0, 0
     ev0.record(stream)
     for i in range(Wm, Wm + K):
@@ -334,11 +376,20 @@ def run_ours(args):
     for i in range(Wm, Wm + K):
         frame_device(i)
         if r1 > r0:
-            tm = ctx.timings()
+            for attempt in range(4):
+                try:
+                    tm = ctx.timings()
+                    break
+                except _lib.SplatError as e:       # this very frame was abandoned on the device: render it again
+                    if e.code != -6 or attempt == 3:
+                        raise
+                    repeats[0] += 1
+                    frame_device(i)
             for k_ in stage:
                 stage[k_] += tm[k_]
             inst_sum += tm["n_instances"]
             cut_sum += tm["near_cut_instances"]
+            second_sum += tm["second_pass_instances"]
             fallbacks += 1 if tm["near_cut_failed"] else 0
             launches += tm["kernel_launches"] + 1       # + the clear
     sync_all()
@@ -455,11 +506,11 @@ def run_ours(args):
                                  "HBM-bound stages are listed in stage_rooflines."},
             "stage_rooflines": stage_roof,
             "stages_ms": ms,
-            "instances_per_frame": I_all, "instances_binned_per_frame": I,
+            "instances_per_frame": I_all, "instances_binned_per_frame": I, "second_pass_instances_per_frame": second_sum / K,
             "near_cut": {"frames_with_fallback": fallbacks, "frames": K,
-                         "note": "first pass bins + sorts only the nearest Gaussians (exact, DESIGN.md); a fall-back frame "
-                                 "re-bins all Gaussians for the tiles that did not converge; stages_ms of such frames "
-                                 "attribute the first pass to bin_ms"},
+                         "note": "first pass bins + sorts only the nearest Gaussians (exact, DESIGN.md); the second pass, gated on "
+                                 "the device, re-bins all Gaussians for the tiles that did not converge (second_pass_ms); "
+                                 "no host wait in either"},
             "frame_checksum": checksum,
         }
         if world == 1 and not args.no_cpu:
@@ -514,6 +565,7 @@ def main():
     ap.add_argument("--near-cut", type=int, default=-1,
                     help="splat_config.near_cut: -1 = automatic (the library default), 0 = off, 1..1024 = fixed fraction")
     ap.add_argument("--equal-stripes", action="store_true", help="N > 1: equal tile-row stripes instead of load-balanced ones")
+    ap.add_argument("--rebalance-rounds", type=int, default=4, help="N > 1: stripe re-cuts from measured per-rank times before the warm-up")
     args = ap.parse_args()
     capture_stdout()
     if args.warmup < 3:

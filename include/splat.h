@@ -111,12 +111,16 @@ typedef struct {
   uint64_t n_instances;  /* (tile, Gaussian) pairs                                  */
   uint64_t n_tiles;      /* tiles in the rendered stripe                            */
   uint64_t kernel_launches; /* kernels launched by the last render                  */
-  uint64_t near_cut_rank;   /* depth ranks below this were left out of the first binning pass (0 = none);
-                             * frames_retried also counts the renders that then needed the complete pass */
+  uint64_t near_cut_rank;   /* depth ranks below this were left out of the first binning pass (0 = none) */
   uint64_t near_cut_failed; /* pixel groups / tiles that did not converge in that pass (0 = it was enough) */
   uint64_t near_cut_instances; /* (tile, Gaussian) pairs that pass did not have to bin and sort */
   uint64_t frames_skipped;  /* since the context was created: frames whose tile instances did not fit the buffers
                              * on the no-round-trip path (host-buffer calls repeat them themselves)            */
+  uint64_t second_pass_instances; /* near-cut frames: (tile, Gaussian) pairs the second pass binned for the tiles that
+                                   * did not converge on the near lists (0 = it had nothing to do)            */
+  uint64_t near_cut_fallbacks;    /* since the context was created: near-cut frames whose second pass had work */
+  float    second_pass_ms;  /* that second pass (included in total_ms)                      */
+  float    reserved_;
 } splat_timings;
 
 uint32_t    splat_abi_version(void);
@@ -139,6 +143,17 @@ int splat_upload_soa(splat_ctx *ctx, const float *pos4, const float *scale3, con
  * repr(C), so the shim copies each Gaussian into 59 consecutive floats:
  * position[3] scale[3] opacity rotation_xyzw[4] sh[48]. */
 int splat_upload_aos(splat_ctx *ctx, const float *gaussians59, uint64_t n);
+
+/* Scene upload straight from a PLY file's vertex payload -- load_from_ply (gaussians.rs:375-405) with
+ * set_property (:258-282) on the device.  vertex_rows: host pointer to n vertices of the INRIA 3DGS
+ * binary_little_endian layout (62 f32: x y z nx ny nz f_dc_0..2 f_rest_0..44 opacity scale_0..2
+ * rot_0..3), stride_floats apart (62 for a plain file).  The device applies exp / sigmoid / the
+ * rot_0 -> w and f_rest_i -> sh[3+i] mappings and subtracts the mean position, accumulated
+ * sequentially in f32 in file order exactly like the reference.  exp is the library's pinned routine
+ * (<= 1 ulp from libm's expf, which Rust calls): activated scales / opacities may differ from the
+ * reference's by one ulp.  activated60 (NULL to skip): receives the activated GaussianList arrays,
+ * n each of pos4 | rot_xyzw | scale3 | opacity | sh48 back to back (tests). */
+int splat_upload_ply_raw(splat_ctx *ctx, const void *vertex_rows, uint64_t n, uint32_t stride_floats, float *activated60);
 
 /* render_to_buffer.  fb_inout: W*H pixels, row-major, 0xAARRGGBB (euc::Buffer<u32,2>::raw(),
  * main.rs:79), blended onto (the caller clears it, main.rs:73) and overwritten.  Synchronous:
@@ -163,12 +178,14 @@ int splat_render_rows(splat_ctx *ctx, const splat_camera *cam, uint32_t *fb_rows
  * context's own stream) and the call returns without waiting for it.
  * The first frame of a target geometry (W, H, row0, row1) blocks once mid-frame to read the
  * tile-instance count and size the buffers.  Every later frame is enqueued with NO host wait: its
- * launches are sized from the previous frame, the kernels read the real count on the device, and
- * the instance buffers are kept at >= 2x the last count.  Should a frame nevertheless want more
- * instances than the buffers hold (its count more than doubled in one frame), it blends NOTHING:
- * its target is left exactly as the caller provided it, and the next call on this context
- * (render or splat_get_timings) grows the buffers and returns SPLAT_ERR_RETRY once -- render that
- * frame again.  The host-buffer entry points repeat such a frame themselves. */
+ * launches are sized from the previous frame (+12.5%), the kernels read the real counts on the
+ * device, and a near-cut frame decides on the device whether its second pass has work.  Should a
+ * frame nevertheless outgrow those bounds, the device abandons it: without a near cut nothing was
+ * blended and the target is exactly as the caller provided it; with a near cut the tiles that had
+ * already converged hold their final pixels and all others are untouched.  The next call on this
+ * context (render or splat_get_timings) grows the buffers and returns SPLAT_ERR_RETRY once: put the
+ * target's previous contents back (e.g. clear it again) and render that frame again.  The
+ * host-buffer entry points do all of that themselves. */
 int splat_render_device(splat_ctx *ctx, const splat_camera *cam, void *fb_rows_dev, uint32_t W,
                         uint32_t H, uint32_t row0, uint32_t row1, void *stream);
 
@@ -234,6 +251,9 @@ int splat_debug_sort_pairs(splat_ctx *ctx, uint32_t *keys, uint32_t *vals, uint6
  * [1] group-entries that changed a pixel, [2] (pixel, Gaussian) pairs with alpha > 0,
  * [3] tile-list entries staged, [4] candidate pairs, [5] pixel-pair lanes with alpha > 0. */
 int splat_debug_blend_stats(splat_ctx *ctx, uint64_t *out8, int reset);
+/* per-tile arrays of the last frame: which = 0 list ranges (2 words per tile), 1 cut Gaussians per tile
+ * (near-cut frames), 2 tiles marked for the second pass */
+int splat_debug_read_tiles(splat_ctx *ctx, int which, uint32_t *out, uint64_t cap_words, uint64_t *n_words);
 /* SPLAT_BLEND_FLOAT contexts: splat_render, plus the un-quantised result of every pixel a fragment
  * contributed to: rgba[4*(y*W+x)] = r, g, b, 1-T (NaN where the pixel was not touched). */
 int splat_debug_render_float(splat_ctx *ctx, const splat_camera *cam, uint32_t *fb_inout, uint32_t W, uint32_t H,

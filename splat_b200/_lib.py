@@ -19,10 +19,10 @@ SPLAT_BLEND_REFERENCE, SPLAT_BLEND_FLOAT = 0, 1
 
 # every symbol include/splat.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = ["splat_abi_version", "splat_config_default", "splat_create", "splat_create_error", "splat_destroy",
-           "splat_last_error", "splat_upload_soa", "splat_upload_aos", "splat_render", "splat_render_cleared",
+           "splat_last_error", "splat_upload_soa", "splat_upload_aos", "splat_upload_ply_raw", "splat_render", "splat_render_cleared",
            "splat_render_rows", "splat_render_device", "splat_get_timings", "splat_get_tile_loads", "splat_pin_host",
            "splat_unpin_host", "splat_debug_project", "splat_debug_read_order",
-           "splat_debug_sort_pairs", "splat_debug_blend_stats", "splat_debug_render_float",
+           "splat_debug_sort_pairs", "splat_debug_blend_stats", "splat_debug_render_float", "splat_debug_read_tiles",
            "splat_create_multi", "splat_group_get_bounds", "splat_comm_unique_id", "splat_comm_init_rank",
            "splat_comm_broadcast_scene", "splat_gather_stripes"]
 
@@ -46,7 +46,8 @@ class SplatTimings(C.Structure):
                 ("d2h_ms", C.c_float), ("frames_retried", C.c_uint32),
                 ("n_gaussians", C.c_uint64), ("n_visible", C.c_uint64), ("n_instances", C.c_uint64),
                 ("n_tiles", C.c_uint64), ("kernel_launches", C.c_uint64), ("near_cut_rank", C.c_uint64), ("near_cut_failed", C.c_uint64), ("near_cut_instances", C.c_uint64),
-                ("frames_skipped", C.c_uint64)]
+                ("frames_skipped", C.c_uint64), ("second_pass_instances", C.c_uint64), ("near_cut_fallbacks", C.c_uint64),
+                ("second_pass_ms", C.c_float), ("reserved_", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -82,6 +83,7 @@ def load():
     L.splat_last_error.restype = C.c_char_p
     L.splat_upload_soa.argtypes = [vp, fp, fp, fp, fp, fp, C.c_uint64]
     L.splat_upload_aos.argtypes = [vp, fp, C.c_uint64]
+    L.splat_upload_ply_raw.argtypes = [vp, vp, C.c_uint64, C.c_uint32, vp]
     L.splat_render.argtypes = [vp, C.POINTER(SplatCamera), vp, C.c_uint32, C.c_uint32]
     L.splat_render_cleared.argtypes = [vp, C.POINTER(SplatCamera), vp, C.c_uint32, C.c_uint32, C.c_uint32]
     L.splat_render_rows.argtypes = [vp, C.POINTER(SplatCamera), vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
@@ -95,6 +97,7 @@ def load():
     L.splat_debug_sort_pairs.argtypes = [vp, vp, vp, C.c_uint64, C.c_int]
     L.splat_debug_blend_stats.argtypes = [vp, vp, C.c_int]
     L.splat_debug_render_float.argtypes = [vp, C.POINTER(SplatCamera), vp, C.c_uint32, C.c_uint32, vp]
+    L.splat_debug_read_tiles.argtypes = [vp, C.c_int, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.splat_create_multi.argtypes = [C.POINTER(vp), C.POINTER(SplatConfig), C.POINTER(C.c_int32), C.c_int32]
     L.splat_group_get_bounds.argtypes = [vp, vp, C.c_int32, C.POINTER(C.c_int32)]
     L.splat_comm_unique_id.argtypes = [vp]
@@ -195,6 +198,22 @@ class Context:
                                             _fp(g.rotations), _fp(g.sh), g.positions.shape[0]))
         self.n = g.positions.shape[0]
 
+    def upload_ply(self, filename: str, want_activated: bool = False):
+        """load_from_ply on the device: the vertex payload of an INRIA-layout binary PLY goes to the GPU as
+        it lies in the file (memory-mapped); activation and recentring happen there.  Returns the activated
+        GaussianList when asked (tests), else None."""
+        from .gaussians import GaussianList, ply_vertex_payload
+
+        rows, n = ply_vertex_payload(filename)          # (n, 62) float32 view of the file
+        act = np.zeros(60 * n, np.float32) if want_activated else None
+        self._check(self.L.splat_upload_ply_raw(self.h, rows.ctypes.data, n, rows.shape[1],
+                                                act.ctypes.data if act is not None else None))
+        self.n = n
+        if act is None:
+            return None
+        pos, rot, sc, op, sh = np.split(act, [4 * n, 8 * n, 11 * n, 12 * n])
+        return GaussianList(pos.reshape(n, 4), sc.reshape(n, 3), op, rot.reshape(n, 4), sh.reshape(n, 48))
+
     def upload_aos(self, g59: np.ndarray):
         self._check(self.L.splat_upload_aos(self.h, _fp(g59), g59.shape[0]))
         self.n = g59.shape[0]
@@ -258,6 +277,15 @@ class Context:
         nv = C.c_uint64()
         self._check(self.L.splat_debug_read_order(self.h, order.ctypes.data, len(order), C.byref(nv)))
         return order[: nv.value].copy()
+
+    def debug_tiles(self, which: int) -> np.ndarray:
+        """per-tile arrays of the last frame (0: ranges (T, 2), 1: far_cnt, 2: tile_failed)"""
+        n = C.c_uint64()
+        t = int(self.timings()["n_tiles"])
+        out = np.zeros(2 * t, np.uint32)
+        self._check(self.L.splat_debug_read_tiles(self.h, which, out.ctypes.data, len(out), C.byref(n)))
+        out = out[: n.value]
+        return out.reshape(-1, 2) if which == 0 else out
 
     def debug_blend_stats(self, reset=True) -> np.ndarray:
         out = np.zeros(8, np.uint64)

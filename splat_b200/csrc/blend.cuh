@@ -183,6 +183,15 @@ SPLAT_DEVINL f32x2 blend_channel2(f32x2 c_old, f32x2 om, f32x2 al, float col, f3
 #ifndef SPLAT_SLEEP_NS_CONSUMER
 #define SPLAT_SLEEP_NS_CONSUMER 32
 #endif
+#ifndef SPLAT_TMA_STAGE
+// 1: stage each batch of the tile list with per-record cp.async.bulk copies (TMA gather) onto one
+// mbarrier; 0: one thread per entry, __ldg + st.shared.  Measured A/B on the bench frame
+// (profiles/r2k_ab_tma_staging.txt): the TMA gather is 3% SLOWER here (blend 0.887 vs 0.863 ms) --
+// a 48-byte copy per instruction keeps the copy engine no busier than the LSU was, and the batch
+// still waits for its slowest record -- so the parity kernel ships the __ldg path; the float
+// compositor (blend_float.cuh), which double-buffers whole batches, uses the TMA gather.
+#define SPLAT_TMA_STAGE 0
+#endif
 #ifndef SPLAT_MAX_PPG_LOG
 #define SPLAT_MAX_PPG_LOG 3   // at most 2^this producer warps evaluate for one group; the rest only stage
 #endif
@@ -288,6 +297,17 @@ SPLAT_DEVINL void mbar_wait(uint64_t *bar, uint32_t parity, const uint32_t *gwor
 SPLAT_DEVINL void mbar_inval(uint64_t *bar) {
   asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+SPLAT_DEVINL void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+// one 1-D bulk copy global -> shared (the TMA engine, no tensor map needed), completion counted in
+// bytes on an mbarrier.  16-byte aligned addresses, size a multiple of 16.
+SPLAT_DEVINL void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 // all threads that take part in a unit (the 8 producer warps + its consumer warps)
 SPLAT_DEVINL void unit_sync(uint32_t nthreads) { asm volatile("bar.sync 2, %0;" ::"r"(nthreads) : "memory"); }
 SPLAT_DEVINL void producers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(BL_PRODUCER_THREADS) : "memory"); }
@@ -383,7 +403,7 @@ struct RingEntry {
   float4 col;      // r, g, b (+ the power threshold, unused by the consumer)
 };
 struct BlendSmem {
-  float4 sa[BL_BATCH], sb[BL_BATCH], sc[BL_BATCH];        // staged records (see Rec)
+  Rec srec[BL_BATCH];                                     // staged records: the tile list's next BL_BATCH entries
   RingEntry ring[BL_SLOTS][BL_CH];                        // chunk slots, BL_SLOTS / ngroups per team
   // ---- the block from here to `trace` is what the watchdog dumps (contiguous on purpose)
   uint64_t full[BL_SLOTS], empty[BL_SLOTS];               // mbarriers
@@ -394,6 +414,7 @@ struct BlendSmem {
   uint8_t list[BL_GROUPS][BL_BATCH];                      // compacted entry indices per group
   uint32_t fail[BL_GROUPS];                               // per team: the suffix attempt did not converge
   uint32_t giveup;                                        // truncated list with a pixel nothing covers
+  uint64_t stage_bar;                                     // mbarrier the TMA gather of a batch completes on
 };
 constexpr size_t BL_SMEM_BYTES = sizeof(BlendSmem);
 
@@ -443,8 +464,12 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
     mbar_init(&S.full[tid], 1);
     mbar_init(&S.empty[tid], 1);
   }
-  if (tid == 0) S.giveup = 0;
+  if (tid == 0) {
+    S.giveup = 0;
+    mbar_init(&S.stage_bar, 1);
+  }
   __syncthreads();
+  uint32_t stage_par = 0;   // phase parity of stage_bar: one phase per staged batch, all attempts
   if (w >= BL_PRODUCER_THREADS / 32 + ng) return;   // split units: the spare consumer warps have nothing to do
   const uint32_t nsync = BL_PRODUCER_THREADS + 32u * ng;   // threads that take part in this unit
   const f32x2 NZ = P.nz2;
@@ -518,11 +543,23 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
       WD_TRACE(1, base - start);
       producers_sync();   // previous batch no longer read by any producer
       uint32_t bits = 0;
+#if SPLAT_TMA_STAGE
+      // TMA gather of the batch: thread j reads list index j and issues ONE bulk copy of that 48-byte
+      // record into shared-memory slot j; all copies complete on one mbarrier (expect_tx = 48 * nb)
+      if (tid == 0) mbar_expect_tx(&S.stage_bar, nb * (uint32_t)sizeof(Rec));
+      if (tid < nb) tma_load_1d(&S.srec[tid], recs + __ldg(&inst_vals[base + tid]), (uint32_t)sizeof(Rec), &S.stage_bar);
+      mbar_wait<SPLAT_WAIT_PRODUCER>(&S.stage_bar, stage_par, n_units, wd, (6u << 28) | ((base - start) & 0xFFFFFu), wdd);
+      stage_par ^= 1u;
+#endif
       if (tid < nb) {
+#if SPLAT_TMA_STAGE
+        const float4 a = S.srec[tid].a, b = S.srec[tid].b, c = S.srec[tid].c;
+#else
         const uint32_t gi = __ldg(&inst_vals[base + tid]);
         const float4 *rp = reinterpret_cast<const float4 *>(recs + gi);
         const float4 a = __ldg(rp), b = __ldg(rp + 1), c = __ldg(rp + 2);
-        S.sa[tid] = a; S.sb[tid] = b; S.sc[tid] = c;
+        S.srec[tid].a = a; S.srec[tid].b = b; S.srec[tid].c = c;
+#endif
         // |RN(s - cxp)| >= RN(dist(cxp, [lo,hi])) for every sample s in [lo,hi] (rounding is
         // monotone), so "dist > h" proves that no pixel of the group passes |dx| <= h.
         uint32_t ox = 0, oy = 0;
@@ -614,7 +651,7 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
 #pragma unroll 2
         for (; s < chunk_end; ++s) {
           const uint32_t j = S.list[g][s - seq];
-          const float4 a = S.sa[j], b = S.sb[j], c = S.sc[j];
+          const float4 a = S.srec[j].a, b = S.srec[j].b, c = S.srec[j].c;
           const float dx = sx - a.x;
           const f32x2 dy2 = sub2(sy2, pk1(a.y));
           float dy0, dy1;

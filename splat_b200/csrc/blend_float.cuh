@@ -40,18 +40,6 @@ struct BlendFloatSmem {
   uint64_t full[BF_STAGES];         // mbarriers: "stage holds batch b"
 };
 
-SPLAT_DEVINL void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-// one 1-D bulk copy global -> shared (the TMA engine, no tensor map needed), completion counted in
-// bytes on an mbarrier.  16-byte aligned addresses, size a multiple of 16.
-SPLAT_DEVINL void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
 __global__ void __launch_bounds__(BF_THREADS)
 blend_float_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units, const uint32_t *__restrict__ n_units,
                    const uint32_t *__restrict__ inst_vals, const Rec *__restrict__ recs, uint32_t *__restrict__ fb_rows,

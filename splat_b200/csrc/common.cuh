@@ -58,10 +58,17 @@ struct FrameStatus {
   unsigned long long n_sort;       // stripe renders: (key, index) pairs that enter the depth sort
   unsigned int n_inst_eff;         // pairs the kernels behind the count process: n_instances, or 0 if they do not fit
   unsigned int overflow;           // this frame wanted more pairs than the instance buffers hold: nothing was blended
+  // near-cut frames, written between the two passes (pass_b_setup_kernel)
+  unsigned long long a_instances;  // pairs the first (near) pass binned
+  unsigned int a_failed;           // units / tiles that did not converge on the near lists
+  unsigned int a_visible;
+  unsigned int a_tag;              // cut_frac the frame was rendered with (0: no cut)
+  unsigned int b_active;           // 1: the second pass (complete lists of the failed tiles) has work
+  unsigned int a_failed_tiles;     // tiles the second pass redoes
   // ---- everything above is zeroed at the start of every frame
   unsigned int skipped;            // frames skipped that way since the context was created (never zeroed)
-  unsigned int pad_;
 };
+static_assert(sizeof(FrameStatus) % 8 == 0, "FrameStatus is copied as a block");
 
 #define SPLAT_DEVINL __device__ __forceinline__
 

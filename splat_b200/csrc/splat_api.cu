@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
+#include <functional>
 #include <new>
 #include <string>
 #include <thread>
@@ -26,6 +27,7 @@
 #include "blend_float.cuh"
 #include "comm.cuh"
 #include "common.cuh"
+#include "ingest.cuh"
 #include "project.cuh"
 #include "sort.cuh"
 
@@ -36,6 +38,7 @@ constexpr uint64_t NEAR_CUT_MIN_VISIBLE = 200000;   // smaller scenes: the cut's
 constexpr size_t FAR_SMEM_MAX = 200 * 1024;            // difference array of far_cover_kernel (shared memory)
 constexpr uint32_t NEAR_CUT_DEFAULT = 128;             // 1/8 of the Gaussians
 enum { EV_START = 0, EV_PROJECT, EV_DSORT, EV_COUNT, EV_EMIT, EV_TSORT, EV_RANGES, EV_BLEND,
+       EV_B_END,                  // near-cut frames: the second pass
        EV_H2D0, EV_H2D1, EV_D2H0, EV_D2H1, EV_COUNT_ };
 }
 
@@ -62,26 +65,40 @@ struct splat_ctx {
   uint2 *ranges = nullptr; size_t ranges_cap = 0;
   uint2 *units = nullptr;          // blend work units, heaviest first (up to 4 per tile)
   uint32_t *far_cnt = nullptr;     // near cut: cut Gaussians per tile
+  uint32_t *tile_open = nullptr;   // near cut: tiles that so few cut Gaussians touch that they are binned for them after all
+  int *open_sat = nullptr;         // summed-area table of tile_open
+  uint2 *rank_rects = nullptr;     // near cut: tile rectangle of the Gaussian at depth rank r (r below the cut)
   uint32_t *tile_failed = nullptr; // near cut: tiles that need the complete lists
   int *far_diff = nullptr;         // its 2-D difference array
   size_t far_cells_cap = 0;
   uint32_t cut_frac = 1024;        // Gaussians binned by the near-cut pass, in 1/1024 (1024 = no cut)
-  uint32_t last_cut = 0;           // rank_cut of the last frame
+  uint32_t frame_cut = 0;          // rank_cut of the frame enqueued last
+  uint32_t frame_cut_seen = 0;     // ... of the frame whose status was absorbed last
+  uint32_t last_cut = 0;           // rank_cut of the last frame whose status the host has seen
   uint32_t last_failed = 0;        // groups / tiles that did not converge in its near-cut pass
+  uint64_t last_second_instances = 0, near_cut_fallbacks = 0, last_full_instances = 0;
   uint64_t last_cut_instances = 0; // (tile, Gaussian) pairs it did not bin
   uint32_t *n_units = nullptr;
   FrameStatus *d_status = nullptr, *h_status = nullptr;
   uint32_t *h_wd = nullptr, *d_wd = nullptr;   // blend watchdog record (mapped pinned host memory, blend.cuh)
   bool debug_sync = false;                     // SPLAT_DEBUG_SYNC=1: bounded wait after every launch, names the kernel that hangs
   double wait_limit_s = 30.0;                  // SPLAT_WAIT_LIMIT_S: bound of every host wait on the device
-  uint32_t *d_fb = nullptr; size_t fb_cap = 0;
+  uint32_t *d_fb = nullptr, *d_fb_bak = nullptr; size_t fb_cap = 0;
 
   float4 *d_tap = nullptr; size_t tap_cap = 0; bool want_tap = false;   // float mode: un-quantised result per pixel (tests)
 
   // last frame
   int order_buf = 0;          // which vals[] holds the depth order
   bool have_frame = false, host_copy = false;
-  bool status_pending = false;   // a frame's status copy is in flight (status_ev)
+  bool status_pending = false;   // some frame's end-of-frame status has not been absorbed yet
+  // End-of-frame statuses land in a small ring (the host may run several frames ahead of the device;
+  // one event re-recorded every frame would never be seen complete while frames keep coming)
+  static constexpr int RING = 4;
+  FrameStatus *h_ring = nullptr;            // RING pinned copies
+  cudaEvent_t ring_ev[RING] = {};
+  bool ring_pending[RING] = {};
+  uint32_t ring_cut[RING] = {};             // rank_cut the frame in that slot was rendered with
+  uint64_t seq = 0;                         // frames enqueued
   bool retry_pending = false;    // a frame was skipped on the device (instance buffers too small) and not yet repeated
   bool loads_valid = false;      // c->ranges describes the complete tile lists of the last frame
   uint32_t skipped_seen = 0;
@@ -103,6 +120,7 @@ struct splat_ctx {
   std::vector<uint32_t> bounds;        // group: stripe rows [2 * members], tile aligned
   uint32_t bounds_geom[2] = {0, 0};    // W, H the bounds were made for
   uint32_t *d_frame = nullptr;         // member: full W x H frame on its device (gather source / target)
+  uint32_t *d_frame_bak = nullptr;     // member: the rows it uploaded, should its stripe have to be repeated
   size_t frame_cap = 0;
   uint32_t frames_since_rebalance = 0;
 };
@@ -187,12 +205,9 @@ int radix_sort(splat_ctx *c, cudaStream_t s, uint32_t *keys[2], uint32_t *vals[2
     const int nbits = std::min(8, bits - shift);
     rs_hist_kernel<<<grid, RS_THREADS, 0, s>>>(keys[cur], n_ptr, n_fixed, shift, (1u << nbits) - 1u, c->hist);
     rs_rowscan_kernel<<<256, RW_THREADS, 0, s>>>(c->hist, n_ptr, n_fixed, c->tot);
-    if (nbits == 8)
-      rs_scatter_kernel<8><<<grid, RS_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1],
-                                                       n_ptr, n_fixed, shift, 8, c->hist, c->tot);
-    else
-      rs_scatter_kernel<0><<<grid, RS_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1],
-                                                       n_ptr, n_fixed, shift, nbits, c->hist, c->tot);
+    uint32_t *ki = keys[cur], *vi = vals[cur], *ko = keys[cur ^ 1], *vo = vals[cur ^ 1];
+    if (nbits == 8) rs_scatter_kernel<8><<<grid, RS_THREADS, 0, s>>>(ki, vi, ko, vo, n_ptr, n_fixed, shift, 8, c->hist, c->tot);
+    else rs_scatter_kernel<0><<<grid, RS_THREADS, 0, s>>>(ki, vi, ko, vo, n_ptr, n_fixed, shift, nbits, c->hist, c->tot);
     c->launches += 2;
     LAUNCHED("radix sort pass (hist, rowscan, scatter)");
     cur ^= 1;
@@ -232,11 +247,13 @@ int ensure_instances(splat_ctx *c, uint64_t want) {
 
 void free_scene(splat_ctx *c) {
   cudaDeviceSynchronize();   // frames may still be in flight on a caller's stream
+  dev_free(c->rank_rects);
   dev_free(c->scene); dev_free(c->recs); dev_free(c->rects); dev_free(c->tcnt); dev_free(c->block_kept); dev_free(c->cnt); dev_free(c->offs);
   for (int k = 0; k < 2; ++k) { dev_free(c->keys[k]); dev_free(c->vals[k]); }
   c->n = 0;
   c->have_frame = false;
   c->status_pending = false;
+  for (int i = 0; i < splat_ctx::RING; ++i) c->ring_pending[i] = false;
   c->retry_pending = false;
   c->loads_valid = false;
 }
@@ -247,6 +264,7 @@ int alloc_scene(splat_ctx *c, uint64_t n) {
   CU(dev_alloc(&c->scene, (size_t)SCENE_PLANES * n));
   CU(dev_alloc(&c->recs, n));
   CU(dev_alloc(&c->rects, n));
+  CU(dev_alloc(&c->rank_rects, n));
   CU(dev_alloc(&c->tcnt, n));
   CU(dev_alloc(&c->block_kept, cdiv(n, 256)));
   CU(dev_alloc(&c->cnt, n));
@@ -293,6 +311,134 @@ __global__ void __launch_bounds__(256) fill_u32_kernel(uint32_t *p, uint32_t v, 
     if (i0 + k < n) p[i0 + k] = v;
 }
 
+// ---------------------------------------------------------------- near cut: the second pass, launched ON THE DEVICE
+// After the first (near) pass of a near-cut frame the device knows which tiles did not converge.
+// pass_b_setup_kernel (bin.cuh) is the only thing the host enqueues for the second pass; if there
+// is work it starts this chain with CUDA dynamic parallelism -- tail launches, which run in order
+// after the launching grid and before the next kernel of the host's stream -- and every launch is
+// sized from the counts the device already holds.  A frame whose near lists sufficed pays one
+// small kernel; nothing is gated, nothing is over-launched, the host never waits.
+struct PassBArgs {
+  FrameStatus *st; uint32_t *tile_failed; int *sat;
+  const uint32_t *sorted_keys, *order, *tcnt, *n_sorted; const uint2 *rects;
+  uint32_t *cnt, *offs, *partial; uint32_t n;
+  uint32_t *ikeys[2], *ivals[2]; uint32_t *hist, *tot; int tile_bits; unsigned long long cap;
+  uint2 *ranges, *units; uint32_t *n_units; uint32_t T;
+  const Rec *recs; uint32_t *fb_rows; uint32_t *wd; float4 *tap; int flt;
+  int diagnose_only;     // SPLAT_NO_SECOND_PASS=1: decide, but launch nothing (tools/near_cut_failures.py; wrong pixels)
+  FrameParams P;
+};
+
+#ifndef SPLAT_CDP
+// 0 (shipped): no device-side launches.  A near-cut frame whose near lists do not suffice is abandoned like one
+// that outgrew its buffers and repeated without the cut -- with OPEN tiles (bin.cuh) that is a rarity (0 of 50
+// frames on the bench orbit).  1 (`make cdp`, needs -rdc=true): the chain below repairs such a frame on the
+// device; -rdc costs every kernel 4-6% (profiles/r2p_ab_cdp_rdc.txt), more than the repair ever saves.
+#define SPLAT_CDP 0
+#endif
+#if SPLAT_CDP
+__global__ void pass_b_stage3_kernel(PassBArgs a, int icur) {
+  const uint32_t nu = *a.n_units;
+  if (nu == 0u) return;
+  if (a.flt)
+    blend_float_kernel<<<nu, BF_THREADS, 0, cudaStreamTailLaunch>>>(a.ranges, a.units, a.n_units, a.ivals[icur], a.recs, a.fb_rows, a.P, a.tap, a.wd);
+  else
+    blend_kernel<<<nu, BL_THREADS, BL_SMEM_BYTES, cudaStreamTailLaunch>>>(a.ranges, a.units, a.n_units, a.ivals[icur], a.recs, a.fb_rows, a.P,
+                                                                         nullptr, a.st, a.tile_failed, a.wd);
+}
+
+__global__ void pass_b_stage2_kernel(PassBArgs a) {
+  const uint32_t I = a.st->n_inst_eff;       // pairs of the failed tiles' complete lists (0: none, or they do not fit)
+  if (I == 0u) return;
+  const uint32_t n = a.n;
+  const cudaStream_t tl = cudaStreamTailLaunch;
+  emit_masked_kernel<<<(n + 255u) / 256u, 256, 0, tl>>>(a.order, a.rects, nullptr, a.cnt, a.offs, a.ikeys[0], a.ivals[0], n, a.P.tiles_x,
+                                                        a.tile_failed, a.sat, &a.st->n_inst_eff);
+  const uint32_t nblk = (I + RS_BLOCK - 1u) / RS_BLOCK;
+  const uint32_t *n_eff = &a.st->n_inst_eff;
+  int cur = 0;
+  for (int shift = 0; shift < a.tile_bits; shift += 8) {
+    const int nbits = min(8, a.tile_bits - shift);
+    rs_hist_kernel<<<nblk, RS_THREADS, 0, tl>>>(a.ikeys[cur], n_eff, 0u, shift, (1u << nbits) - 1u, a.hist);
+    rs_rowscan_kernel<<<256, RW_THREADS, 0, tl>>>(a.hist, n_eff, 0u, a.tot);
+    if (nbits == 8) rs_scatter_kernel<8><<<nblk, RS_THREADS, 0, tl>>>(a.ikeys[cur], a.ivals[cur], a.ikeys[cur ^ 1], a.ivals[cur ^ 1], n_eff, 0u, shift, 8, a.hist, a.tot);
+    else rs_scatter_kernel<0><<<nblk, RS_THREADS, 0, tl>>>(a.ikeys[cur], a.ivals[cur], a.ikeys[cur ^ 1], a.ivals[cur ^ 1], n_eff, 0u, shift, nbits, a.hist, a.tot);
+    cur ^= 1;
+  }
+  fill_u32_kernel<<<(2u * a.T + 1023u) / 1024u, 256, 0, tl>>>(reinterpret_cast<uint32_t *>(a.ranges), 0u, (size_t)2u * a.T);
+  tile_ranges_kernel<<<(I + 1023u) / 1024u, 256, 0, tl>>>(a.ikeys[cur], n_eff, a.ranges);
+  unit_order_kernel<<<1, 1024, 0, tl>>>(a.ranges, a.T, a.units, a.n_units, &a.st->n_instances, nullptr, a.st, a.P.tiles_x, a.tile_failed, 1, a.flt);
+  pass_b_stage3_kernel<<<1, 1, 0, tl>>>(a, cur);
+}
+
+// launched by the LAST thread of pass_b_setup_kernel when the second pass has work
+__device__ void pass_b_launch(const PassBArgs &a) {
+  const uint32_t n = a.n;
+  const cudaStream_t tl = cudaStreamTailLaunch;
+  tile_count_kernel<<<(n + 255u) / 256u, 256, 0, tl>>>(a.sorted_keys, a.order, a.tcnt, a.cnt, n, a.n_sorted, 0u, a.st, a.rects, a.sat, a.P.tiles_x + 1u,
+                                                       nullptr, nullptr);
+  const uint32_t np = max(1u, (n + SC_BLOCK - 1u) / SC_BLOCK);
+  scan_reduce_kernel<<<np, SC_THREADS, 0, tl>>>(a.cnt, a.partial, n);
+  scan_partials_kernel<<<1, 1024, 0, tl>>>(a.partial, np, &a.st->n_instances, a.st, a.cap, &a.st->n_inst_eff, false);
+  scan_apply_kernel<<<np, SC_THREADS, 0, tl>>>(a.cnt, a.offs, a.partial, n);
+  pass_b_stage2_kernel<<<1, 1, 0, tl>>>(a);
+}
+#endif
+
+// Between the two passes of a near-cut frame, on the device (one CTA): did the near lists suffice?
+// Saves the first pass's counters and, if some tiles did not converge, builds the summed-area table
+// of the failed-tile bitmap that the second pass bins against and launches that pass.  If the
+// first pass binned nothing at all, every tile is redone.
+__global__ void __launch_bounds__(1024)
+pass_b_setup_kernel(PassBArgs a, uint32_t tag) {
+  extern __shared__ int s_sat[];
+  FrameStatus *st = a.st;
+  const uint32_t tiles_x = a.P.tiles_x, tiles_y = a.P.tiles_y;
+  const uint32_t pitch = tiles_x + 1u, cells = pitch * (tiles_y + 1u), T = tiles_x * tiles_y;
+  const bool nothing = st->n_instances == 0ull;
+  const bool active = (st->n_failed != 0u || nothing) && st->overflow == 0u;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st->a_instances = st->n_instances;
+    st->a_failed = nothing ? T : st->n_failed;
+    st->a_visible = st->n_visible;
+    st->a_tag = tag;
+    st->b_active = active ? 1u : 0u;
+    st->n_instances = 0ull;
+    st->n_visible = 0u;
+    st->n_failed = 0u;
+    st->n_inst_eff = 0u;
+  }
+  if (!active) return;
+  for (uint32_t i = threadIdx.x; i < cells; i += blockDim.x) s_sat[i] = 0;
+  __syncthreads();
+  for (uint32_t t = threadIdx.x; t < T; t += blockDim.x) {
+    if (nothing) a.tile_failed[t] = 1u;
+    s_sat[(t / tiles_x + 1u) * pitch + (t % tiles_x) + 1u] = (nothing || a.tile_failed[t]) ? 1 : 0;
+  }
+  __syncthreads();
+  for (uint32_t y = 1u + threadIdx.x; y <= tiles_y; y += blockDim.x) {     // along x, one row per thread
+    int run = 0;
+    for (uint32_t x = 1; x <= tiles_x; ++x) { run += s_sat[y * pitch + x]; s_sat[y * pitch + x] = run; }
+  }
+  __syncthreads();
+  for (uint32_t x = 1u + threadIdx.x; x <= tiles_x; x += blockDim.x) {     // along y, one column per thread
+    int run = 0;
+    for (uint32_t y = 1; y <= tiles_y; ++y) { run += s_sat[y * pitch + x]; s_sat[y * pitch + x] = run; }
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < cells; i += blockDim.x) a.sat[i] = s_sat[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st->a_failed_tiles = (uint32_t)s_sat[tiles_y * pitch + tiles_x];
+#if SPLAT_CDP
+    if (!a.diagnose_only) pass_b_launch(a);
+#else
+    if (!a.diagnose_only) { st->overflow = 1u; st->skipped += 1u; }
+#endif
+  }
+}
+
 int ilog2_ceil(uint32_t v) {
   int b = 0;
   while ((1ull << b) < v) ++b;
@@ -301,20 +447,53 @@ int ilog2_ceil(uint32_t v) {
 
 // What the host learnt from a finished frame's status block (copied to pinned memory behind the
 // blend kernel).  Called wherever the host has waited for the frame anyway, or finds it finished.
-void absorb_status(splat_ctx *c) {
-  const FrameStatus &fs = *c->h_status;
-  c->last_instances = fs.n_instances;
-  c->last_visible = fs.n_visible;
+void absorb_slot(splat_ctx *c, int slot) {
+  const FrameStatus &fs = c->h_ring[slot];
+  c->frame_cut_seen = c->ring_cut[slot];
+  c->ring_pending[slot] = false;
+  const bool cut = fs.a_tag != 0u;               // a near-cut frame: the first pass's counters were saved on the device
+  c->last_instances = cut ? fs.a_instances : fs.n_instances;
+  c->last_visible = cut ? fs.a_visible : fs.n_visible;
   c->last_sort = fs.n_sort;
+  c->last_cut = cut ? c->frame_cut_seen : 0u;
+  c->last_failed = cut ? fs.a_failed : 0u;
+  c->last_cut_instances = cut ? fs.n_cut : 0ull;
+  c->last_second_instances = cut ? fs.n_instances : 0ull;
+  if (cut && fs.b_active) c->near_cut_fallbacks += 1;
+  c->last_full_instances = cut ? fs.a_instances + fs.n_cut : fs.n_instances;   // pairs of the complete lists
+  // automatic mode: the near lists did not suffice (a repeated frame costs more than the cut saves; with the
+  // device-launched second pass: it had to bin more than an eighth of what the cut saved, or more than half
+  // of the tiles) -> keep twice as many Gaussians in the first pass from now on
+  if (cut && c->cfg.near_cut < 0 && fs.a_tag == c->cut_frac &&
+      (SPLAT_CDP ? ((uint64_t)fs.a_failed_tiles * 2u > c->last_tiles || fs.n_instances * 8ull > fs.n_cut) : fs.b_active != 0u))
+    c->cut_frac = std::min<uint32_t>(1024u, c->cut_frac * 2u);
   if (fs.skipped != c->skipped_seen) {          // a frame (or several) wanted more pairs than the buffers hold
     c->frames_skipped += fs.skipped - c->skipped_seen;
     c->skipped_seen = fs.skipped;
     c->retry_pending = true;
   }
-  c->status_pending = false;
+}
+// absorb, oldest first, every status whose copy has landed (all = true: the caller has waited for the
+// last frame, so all of them have)
+void absorb_status(splat_ctx *c, bool all = true) {
+  bool any = false;
+  for (uint64_t q = c->seq >= (uint64_t)splat_ctx::RING ? c->seq - splat_ctx::RING : 0; q < c->seq; ++q) {
+    const int slot = (int)(q % splat_ctx::RING);
+    if (!c->ring_pending[slot]) continue;
+    if (all || cudaEventQuery(c->ring_ev[slot]) == cudaSuccess) absorb_slot(c, slot);
+    else any = true;
+  }
+  c->status_pending = any;
 }
 void poll_status(splat_ctx *c) {
-  if (c->status_pending && cudaEventQuery(c->status_ev) == cudaSuccess) absorb_status(c);
+  if (c->status_pending) absorb_status(c, false);
+}
+cudaEvent_t last_status_event(splat_ctx *c) { return c->ring_ev[(c->seq + splat_ctx::RING - 1) % splat_ctx::RING]; }
+
+// capacity to grow the instance buffers to after a frame did not fit: the largest count any pass of it wanted, +50%
+uint64_t grow_target(const splat_ctx *c) {
+  const uint64_t w = std::max(std::max(c->last_instances, c->last_full_instances), c->last_second_instances);
+  return w + w / 2 + 65536u;
 }
 
 // pairs the depth sort of a frame is launched for: all Gaussians, or (stripe frames the host has
@@ -325,59 +504,56 @@ uint64_t sort_bound_all(const splat_ctx *c, const FrameParams &, bool async, uin
 
 struct Pass {
   uint32_t rank_cut = 0;            // near cut: depth ranks below this get no instances (0 = complete lists)
-  const TileRect *only_box = nullptr;
-  bool only_failed = false;
   bool sync_count = true;           // host reads the instance count mid-frame (exact grids, buffers grown on the spot)
 };
 
-// Second half of a frame on `s`: bin the Gaussians of depth rank >= rank_cut into tiles, sort the
-// instances by tile, blend.
+// Second half of a frame on `s`: bin the Gaussians into tiles, sort the instances by tile, blend.
 //   sync_count = true : the host waits for the instance count (one round trip), grows the buffers if
-//                       needed and sizes the launches exactly.  First frame of a target geometry,
-//                       near-cut frames, and the repeat of a skipped frame.
+//                       needed and sizes the launches exactly.  First frame of a target geometry and
+//                       the repeat of a skipped frame.
 //   sync_count = false: nothing blocks.  Launches are sized from the previous frame (+12.5%); the
 //                       kernels read the count from device memory, and a frame whose pairs do not
 //                       fit that bound blends NOTHING (status.overflow) and is repeated by the host.
+// With rank_cut this is the first pass of a near-cut frame; enqueue_second_pass follows it.
 int bin_sort_blend(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cudaStream_t s, cudaEvent_t wait_ev,
                    int cur, const uint32_t *n_sorted, const Pass &pass) {
-  TileRect box;                      // tiles this pass bins into (stripe-local tile coordinates)
-  box.x0 = 0; box.y0 = 0; box.x1 = 0xFFFF; box.y1 = 0xFFFF;
-  if (pass.only_box) box = *pass.only_box;
   const uint32_t rank_cut = pass.rank_cut;
   const uint32_t n = c->n;
   const uint32_t T = P.tiles_x * P.tiles_y;
   const bool flt = c->cfg.blend_mode == SPLAT_BLEND_FLOAT;
+  const size_t cells = (size_t)(P.tiles_x + 1) * (P.tiles_y + 1);   // not a function of T alone
   if (T > c->ranges_cap) {
     CU(cudaStreamSynchronize(s));
     dev_free(c->ranges);
     dev_free(c->units);
     dev_free(c->far_cnt);
     dev_free(c->tile_failed);
+    dev_free(c->tile_open);
+    CU(dev_alloc(&c->tile_open, T));
     CU(dev_alloc(&c->ranges, T));
     CU(dev_alloc(&c->units, (size_t)4 * T));
     CU(dev_alloc(&c->far_cnt, T));
     CU(dev_alloc(&c->tile_failed, T));
     c->ranges_cap = T;
   }
-  {
-    const size_t cells = (size_t)(P.tiles_x + 1) * (P.tiles_y + 1);   // not a function of T alone
-    if (cells > c->far_cells_cap) {
-      CU(cudaStreamSynchronize(s));
-      dev_free(c->far_diff);
-      CU(dev_alloc(&c->far_diff, cells));
-      c->far_cells_cap = cells;
-    }
+  if (cells > c->far_cells_cap) {
+    CU(cudaStreamSynchronize(s));
+    dev_free(c->far_diff);
+    dev_free(c->open_sat);
+    CU(dev_alloc(&c->far_diff, cells));
+    CU(dev_alloc(&c->open_sat, cells));
+    c->far_cells_cap = cells;
   }
   // n_instances, n_visible, n_failed, fail box, n_cut (the fields behind them belong to the frame)
   CU(cudaMemsetAsync(c->d_status, 0, offsetof(FrameStatus, n_sort), s));
   const uint32_t *far = nullptr;
   if (rank_cut) {
-    const size_t cells = (size_t)(P.tiles_x + 1) * (P.tiles_y + 1);
     CU(cudaMemsetAsync(c->far_diff, 0, cells * sizeof(int), s));
     CU(cudaMemsetAsync(c->tile_failed, 0, (size_t)T * sizeof(uint32_t), s));
     far_cover_kernel<<<148, FC_THREADS, cells * sizeof(int), s>>>(c->vals[cur], c->rects, n_sorted, n, rank_cut,
-                                                                  P.tiles_x, P.tiles_y, c->far_diff);
-    far_prefix_kernel<<<1, 1024, cells * sizeof(int), s>>>(c->far_diff, P.tiles_x, P.tiles_y, c->far_cnt, c->d_status);
+                                                                  P.tiles_x, P.tiles_y, c->far_diff, c->rank_rects);
+    far_prefix_kernel<<<1, 1024, cells * sizeof(int), s>>>(c->far_diff, P.tiles_x, P.tiles_y, c->far_cnt, c->d_status,
+                                                           c->tile_open, c->open_sat);
     c->launches += 1;
     LAUNCHED("far_cover / far_prefix");
     far = c->far_cnt;
@@ -386,10 +562,11 @@ int bin_sort_blend(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cu
   // frame that wants more is skipped on the device (overflow) and repeated with a round trip
   const uint64_t n_bound = std::min<uint64_t>(c->inst_cap, c->last_instances + c->last_instances / 8 + 65536u);
   tile_count_kernel<<<cdiv(n, 256), 256, 0, s>>>(c->keys[cur], c->vals[cur], c->tcnt, c->cnt, n, n_sorted, rank_cut, c->d_status,
-                                                  pass.only_box ? c->rects : nullptr, box);
+                                                  nullptr, nullptr, P.tiles_x + 1u, rank_cut ? c->rank_rects : nullptr,
+                                                  rank_cut ? c->open_sat : nullptr);
   LAUNCHED("tile_count_kernel");
-  // exclusive scan cnt -> offs; grand total -> status.n_instances, checked against the buffer
-  // capacity on the device (status.n_inst_eff / overflow)
+  // exclusive scan cnt -> offs; grand total -> status.n_instances, checked against the bound on the
+  // device (status.n_inst_eff / overflow)
   {
     const uint32_t np = std::max(1u, cdiv(n, SC_BLOCK));
     scan_reduce_kernel<<<np, SC_THREADS, 0, s>>>(c->cnt, c->partial, n);
@@ -407,6 +584,7 @@ int bin_sort_blend(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cu
     { int rcw = wait_done(c, c->status_ev, s, "tile count (first half of the frame)"); if (rcw) return rcw; }
     const uint64_t I = c->h_status->n_instances;
     c->last_instances = I;
+    c->last_full_instances = I;
     c->last_visible = c->h_status->n_visible;
     c->last_sort = c->h_status->n_sort;
     if (I >= 0xFFFFFFFEull) return fail(c, SPLAT_ERR_UNSUPPORTED, "more than 2^32-2 tile instances in one stripe");
@@ -422,7 +600,10 @@ int bin_sort_blend(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cu
   c->last_tiles = (uint64_t)T;
   const uint32_t *n_eff = &c->d_status->n_inst_eff;
   emit_instances_kernel<<<cdiv(n, 256), 256, 0, s>>>(c->vals[cur], c->rects, c->cnt, c->offs,
-                                                      c->ikeys[0], c->ivals[0], n, P.tiles_x, box, n_eff);
+                                                      c->ikeys[0], c->ivals[0], n, P.tiles_x, n_eff, rank_cut);
+  if (rank_cut)   // the cut Gaussians' few instances in the open tiles
+    emit_masked_kernel<<<cdiv(rank_cut, 256), 256, 0, s>>>(c->vals[cur], c->rects, c->rank_rects, c->cnt, c->offs, c->ikeys[0], c->ivals[0],
+                                                           rank_cut, P.tiles_x, c->tile_open, c->open_sat, n_eff);
   LAUNCHED("emit_instances_kernel");
   CU(cudaEventRecord(c->ev[EV_EMIT], s));
   int icur = 0;
@@ -433,7 +614,7 @@ int bin_sort_blend(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cu
   tile_ranges_kernel<<<std::max(1u, std::min(cdiv(n_grid, 1024), 1u << 20)), 256, 0, s>>>(c->ikeys[icur], n_eff, c->ranges);
   LAUNCHED("tile_ranges_kernel");
   unit_order_kernel<<<1, 1024, 0, s>>>(c->ranges, T, c->units, c->n_units, &c->d_status->n_instances, far, c->d_status, P.tiles_x,
-                                       c->tile_failed, pass.only_failed ? 1 : 0, flt ? 1 : 0);   // heaviest first
+                                       c->tile_failed, 0, flt ? 1 : 0);   // heaviest first
   LAUNCHED("unit_order_kernel");
   CU(cudaEventRecord(c->ev[EV_RANGES], s));
   if (wait_ev) CU(cudaStreamWaitEvent(s, wait_ev, 0));
@@ -447,13 +628,30 @@ int bin_sort_blend(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cu
     LAUNCHED("blend_kernel");
   }
   CU(cudaEventRecord(c->ev[EV_BLEND], s));
-  CU(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(FrameStatus), cudaMemcpyDeviceToHost, s));
-  CU(cudaEventRecord(c->status_ev, s));
-  c->status_pending = true;
-  if (rank_cut) {
-    { int rcw = wait_done(c, c->status_ev, s, "near-cut pass (bin, sort, blend)"); if (rcw) return rcw; }   // did every pixel converge on the near lists?
-    c->status_pending = false;
-  }
+  return SPLAT_OK;
+}
+
+// Near-cut frames: ONE kernel decides on the device whether the near lists sufficed and, if not,
+// launches the second pass itself (pass_b_setup_kernel above).
+int enqueue_second_pass(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cudaStream_t s, int cur, const uint32_t *n_sorted) {
+  PassBArgs a;
+  a.st = c->d_status; a.tile_failed = c->tile_failed; a.sat = c->far_diff;
+  a.sorted_keys = c->keys[cur]; a.order = c->vals[cur]; a.tcnt = c->tcnt; a.n_sorted = n_sorted; a.rects = c->rects;
+  a.cnt = c->cnt; a.offs = c->offs; a.partial = c->partial; a.n = c->n;
+  for (int k = 0; k < 2; ++k) { a.ikeys[k] = c->ikeys[k]; a.ivals[k] = c->ivals[k]; }
+  a.hist = c->hist; a.tot = c->tot;
+  a.T = P.tiles_x * P.tiles_y;
+  a.tile_bits = ilog2_ceil(a.T);
+  a.cap = c->inst_cap;
+  a.ranges = c->ranges; a.units = c->units; a.n_units = c->n_units;
+  a.recs = c->recs; a.fb_rows = fb_rows_dev; a.wd = c->d_wd; a.tap = nullptr;
+  a.flt = c->cfg.blend_mode == SPLAT_BLEND_FLOAT ? 1 : 0;
+  a.diagnose_only = std::getenv("SPLAT_NO_SECOND_PASS") ? 1 : 0;
+  a.P = P;
+  const size_t cells = (size_t)(P.tiles_x + 1) * (P.tiles_y + 1);
+  pass_b_setup_kernel<<<1, 1024, cells * sizeof(int), s>>>(a, c->cut_frac);
+  LAUNCHED("pass_b_setup_kernel (+ the second pass it launches)");
+  CU(cudaEventRecord(c->ev[EV_B_END], s));
   return SPLAT_OK;
 }
 
@@ -475,16 +673,25 @@ int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cuda
   uint32_t rank_cut = 0;
   const size_t far_smem = (size_t)(P.tiles_x + 1) * (P.tiles_y + 1) * sizeof(int);
   const uint64_t min_visible = c->cfg.near_cut > 0 ? 1u : NEAR_CUT_MIN_VISIBLE;   // a fixed fraction is honoured on any scene (tests)
-  if (c->cut_frac < 1024u && c->have_frame && c->last_visible >= min_visible && far_smem <= FAR_SMEM_MAX) {
+  // automatic mode only where it pays and is safe: tile lists of >= 2048 entries on average, so that the
+  // nearest eighth still holds a few hundred entries per tile
+  const bool long_lists = c->cfg.near_cut > 0 || c->last_full_instances >= 2048ull * P.tiles_x * P.tiles_y;
+  if (c->cut_frac < 1024u && c->have_frame && c->last_visible >= min_visible && long_lists && far_smem <= FAR_SMEM_MAX) {
     const uint64_t keep = (c->last_visible * c->cut_frac + 1023u) / 1024u;
     if (keep < c->last_visible) rank_cut = (uint32_t)(c->last_visible - keep);
   }
-  // near-cut frames read their status on the host (did every pixel converge?); all others need no host wait
-  bool async = same_geom && !force_sync && !c->retry_pending && rank_cut == 0 && !c->cfg.sync_frames;
-  if (async && c->last_instances + c->last_instances / 8 + 65536u > c->inst_cap) {
-    // cudaFree / cudaMalloc wait for the frames in flight; rare (the buffers are grown with 25% headroom)
-    int rc = ensure_instances(c, c->last_instances + c->last_instances / 8 + 65536u);
-    if (rc) return rc;
+  // a frame with a host round trip (first of a geometry, repeat of a skipped one) bins everything
+  bool async = same_geom && !force_sync && !c->retry_pending && !c->cfg.sync_frames;
+  if (!async) rank_cut = 0;
+  {
+    // the buffers must hold this frame's pairs: the first pass's (+12.5%), and -- near-cut frames --
+    // whatever the second pass may want, up to the complete lists.  cudaFree / cudaMalloc wait for the
+    // frames in flight; rare (the buffers are grown with 25% headroom)
+    const uint64_t want = rank_cut ? c->last_full_instances + c->last_full_instances / 4 : c->last_instances;
+    if (async && want + want / 8 + 65536u > c->inst_cap) {
+      int rc = ensure_instances(c, want + want / 8 + 65536u);
+      if (rc) return rc;
+    }
   }
   CU(cudaEventRecord(c->ev[EV_START], s));
   CU(cudaMemsetAsync(c->d_status, 0, offsetof(FrameStatus, skipped), s));
@@ -524,35 +731,26 @@ int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cuda
   pass.sync_count = !async;
   int rc = bin_sort_blend(c, P, fb_rows_dev, s, wait_ev, cur, n_sorted, pass);
   if (rc) return rc;
-  c->last_cut = rank_cut;
-  c->last_failed = rank_cut ? c->h_status->n_failed : 0u;
-  c->last_cut_instances = rank_cut ? c->h_status->n_cut : 0ull;
-  c->loads_valid = true;
-  if (rank_cut && (c->h_status->n_failed != 0 || c->h_status->n_instances == 0)) {
-    // The near lists were not enough for this view: bin + sort + blend again with ALL Gaussians,
-    // restricted to the bounding box of the tiles that did not converge when that box is small
-    // (typically a strip along one screen edge).  Groups that already converged wrote final values
-    // and, if they are blended again, converge to them again without reading the framebuffer;
-    // groups that did not converge left their pixels untouched.
-    const FrameStatus fs = *c->h_status;
-    TileRect fbx;
-    fbx.x0 = (uint16_t)~fs.fail_ix0; fbx.y0 = (uint16_t)~fs.fail_iy0;
-    fbx.x1 = (uint16_t)fs.fail_x1;   fbx.y1 = (uint16_t)fs.fail_y1;
-    const bool have_box = fs.n_failed != 0 && fs.n_instances != 0 && fbx.x1 >= fbx.x0 && fbx.y1 >= fbx.y0;
-    const uint64_t area = have_box ? (uint64_t)(fbx.x1 - fbx.x0 + 1) * (fbx.y1 - fbx.y0 + 1) : ~0ull;
-    const bool partial = have_box && area * 2u <= (uint64_t)P.tiles_x * P.tiles_y;
-    if (!partial && c->cfg.near_cut < 0) c->cut_frac = std::min<uint32_t>(1024u, c->cut_frac * 2u);
-    c->retried += 1;
-    const uint64_t near_instances = fs.n_instances;
-    Pass again;
-    again.only_box = partial ? &fbx : nullptr;
-    again.only_failed = fs.n_instances != 0;
-    rc = bin_sort_blend(c, P, fb_rows_dev, s, wait_ev, cur, n_sorted, again);
+  c->loads_valid = rank_cut == 0;
+  if (rank_cut) {
+    // The second pass decides ON THE DEVICE whether it has work (and launches itself): if some tiles
+    // did not converge on the near lists, they -- and only they -- are binned, sorted and blended
+    // again with ALL Gaussians.  Groups that already converged wrote final values and, blended again,
+    // converge to them again without reading the framebuffer; groups that did not converge left
+    // their pixels untouched.
+    rc = enqueue_second_pass(c, P, fb_rows_dev, s, cur, n_sorted);
     if (rc) return rc;
-    if (partial) {
-      c->last_instances += near_instances;     // both passes' instances were binned and sorted
-      c->loads_valid = false;                   // c->ranges holds the box-restricted lists only
-    }
+  }
+  c->frame_cut = rank_cut;
+  {
+    const int slot = (int)(c->seq % splat_ctx::RING);
+    if (c->ring_pending[slot] && cudaEventQuery(c->ring_ev[slot]) == cudaSuccess) absorb_slot(c, slot);   // else: dropped
+    CU(cudaMemcpyAsync(&c->h_ring[slot], c->d_status, sizeof(FrameStatus), cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(c->ring_ev[slot], s));
+    c->ring_pending[slot] = true;
+    c->ring_cut[slot] = rank_cut;
+    c->seq += 1;
+    c->status_pending = true;
   }
   CU(cudaGetLastError());
   c->have_frame = true;
@@ -568,18 +766,18 @@ int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cuda
 int finish_frame(splat_ctx *c) {
   if (!c->have_frame) return SPLAT_OK;
   if (c->status_pending) {
-    int rc = wait_done(c, c->status_ev, c->last_stream, "frame");
+    int rc = wait_done(c, last_status_event(c), c->last_stream, "frame");
     if (rc) return rc;
     absorb_status(c);
   }
   for (int tries = 0; c->retry_pending && tries < 3; ++tries) {
     c->retry_pending = false;
     c->retried += 1;
-    int rc = ensure_instances(c, c->last_instances + c->last_instances / 4 + 65536u);
+    int rc = ensure_instances(c, grow_target(c));
     if (rc) return rc;
     rc = render_frame(c, c->last_params, c->last_fb, c->last_stream, nullptr, true);
     if (rc) return rc;
-    rc = wait_done(c, c->status_ev, c->last_stream, "frame (repeat)");
+    rc = wait_done(c, last_status_event(c), c->last_stream, "frame (repeat)");
     if (rc) return rc;
     absorb_status(c);
   }
@@ -652,7 +850,9 @@ int ensure_frame(splat_ctx *m, size_t px) {
   if (px <= m->frame_cap) return SPLAT_OK;
   CU(cudaDeviceSynchronize());
   dev_free(m->d_frame);
+  dev_free(m->d_frame_bak);
   CU(dev_alloc(&m->d_frame, px));
+  CU(dev_alloc(&m->d_frame_bak, px));
   m->frame_cap = px;
   return SPLAT_OK;
 }
@@ -702,7 +902,7 @@ int group_render(splat_ctx *g, const splat_camera *cam, uint32_t *fb, uint32_t W
   const size_t px = (size_t)W * H;
   std::vector<char> todo((size_t)G, 1);     // members whose stripe still has to be rendered
   for (int attempt = 0; attempt < 3; ++attempt) {
-    // enqueue: upload / clear (first attempt only: a skipped stripe left its rows untouched), kernels
+    // enqueue: upload / clear, kernels (a repeated stripe starts from the caller's pixels again)
     for (int k = 0; k < G; ++k) {
       splat_ctx *m = g->members[k];
       const uint32_t r0 = g->bounds[2 * k], r1 = g->bounds[2 * k + 1];
@@ -717,10 +917,12 @@ int group_render(splat_ctx *g, const splat_camera *cam, uint32_t *fb, uint32_t W
       const size_t bytes = (size_t)(r1 - r0) * W * 4u;
       cudaEvent_t wait_ev = nullptr;
       CU(cudaEventRecord(m->ev[EV_H2D0], m->copy_stream));
-      if (attempt > 0) {
-        // rows are still as uploaded / cleared
+      if (clear_value < 0 && attempt > 0) {
+        // the download overwrote the caller's pixels: the member kept a copy of what it uploaded
+        CU(cudaMemcpyAsync(rows, m->d_frame_bak + (size_t)r0 * W, bytes, cudaMemcpyDeviceToDevice, m->copy_stream));
       } else if (clear_value < 0) {
         CU(cudaMemcpyAsync(rows, fb + (size_t)r0 * W, bytes, cudaMemcpyHostToDevice, m->copy_stream));
+        CU(cudaMemcpyAsync(m->d_frame_bak + (size_t)r0 * W, rows, bytes, cudaMemcpyDeviceToDevice, m->copy_stream));
       } else if (clear_value == 0 || (((uint32_t)clear_value & 0xFFu) * 0x01010101u) == (uint32_t)clear_value) {
         CU(cudaMemsetAsync(rows, (int)((uint32_t)clear_value & 0xFFu), bytes, m->copy_stream));
       } else {
@@ -742,6 +944,14 @@ int group_render(splat_ctx *g, const splat_camera *cam, uint32_t *fb, uint32_t W
     NC(N->GroupEnd());
     splat_ctx *root = g->members[0];
     CU(cudaSetDevice(root->cfg.device));
+    if (attempt == 0 && clear_value < 0) {
+      // the members members' uploads read the caller's buffer: they must be done before the download writes it
+      for (int k = 0; k < G; ++k) {
+        CU(cudaSetDevice(g->members[k]->cfg.device));
+        CU(cudaStreamSynchronize(g->members[k]->copy_stream));
+      }
+      CU(cudaSetDevice(root->cfg.device));
+    }
     CU(cudaEventRecord(root->ev[EV_D2H0], root->stream));
     CU(cudaMemcpyAsync(fb, root->d_frame, px * 4u, cudaMemcpyDeviceToHost, root->stream));
     CU(cudaEventRecord(root->ev[EV_D2H1], root->stream));
@@ -756,7 +966,7 @@ int group_render(splat_ctx *g, const splat_camera *cam, uint32_t *fb, uint32_t W
       todo[k] = 0;
       if (m->retry_pending) {          // this member's stripe was skipped on the device: grow, render it again
         m->retry_pending = false;
-        rc = ensure_instances(m, m->last_instances + m->last_instances / 4 + 65536u);
+        rc = ensure_instances(m, grow_target(m));
         if (rc) { g->err = m->err; return rc; }
         todo[k] = 1;
         again = true;
@@ -868,12 +1078,18 @@ int splat_create(splat_ctx **out, const splat_config *cfg) {
     return bail(SPLAT_ERR_CUDA);
   if (cudaFuncSetAttribute(far_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAR_SMEM_MAX) != cudaSuccess)
     return bail(SPLAT_ERR_CUDA);
+  if (cudaFuncSetAttribute(pass_b_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAR_SMEM_MAX) != cudaSuccess)
+    return bail(SPLAT_ERR_CUDA);
   if (dev_alloc(&c->d_status, 1) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
   if (cudaMemset(c->d_status, 0, sizeof(FrameStatus)) != cudaSuccess) return bail(SPLAT_ERR_CUDA);
   if (dev_alloc(&c->n_units, 1) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
   if (dev_alloc(&c->tot, 256) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
   if (cudaMallocHost(reinterpret_cast<void **>(&c->h_status), sizeof(FrameStatus)) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
   std::memset(c->h_status, 0, sizeof(FrameStatus));
+  if (cudaMallocHost(reinterpret_cast<void **>(&c->h_ring), splat_ctx::RING * sizeof(FrameStatus)) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
+  std::memset(c->h_ring, 0, splat_ctx::RING * sizeof(FrameStatus));
+  for (int i = 0; i < splat_ctx::RING; ++i)
+    if (cudaEventCreateWithFlags(&c->ring_ev[i], cudaEventDisableTiming) != cudaSuccess) return bail(SPLAT_ERR_CUDA);
   if (cudaHostAlloc(reinterpret_cast<void **>(&c->h_wd), WD_WORDS * sizeof(uint32_t), cudaHostAllocMapped) != cudaSuccess) return bail(SPLAT_ERR_NOMEM);
   std::memset(c->h_wd, 0, WD_WORDS * sizeof(uint32_t));
   if (cudaHostGetDevicePointer(reinterpret_cast<void **>(&c->d_wd), c->h_wd, 0) != cudaSuccess) return bail(SPLAT_ERR_CUDA);
@@ -897,11 +1113,14 @@ void splat_destroy(splat_ctx *c) {
     c->comm = nullptr;
   }
   dev_free(c->d_frame);
+  dev_free(c->d_frame_bak);
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_scene(c);
-  dev_free(c->hist); dev_free(c->tot); dev_free(c->partial); dev_free(c->ranges); dev_free(c->units); dev_free(c->far_cnt); dev_free(c->far_diff); dev_free(c->tile_failed); dev_free(c->n_units); dev_free(c->d_status); dev_free(c->d_fb); dev_free(c->d_tap);
+  dev_free(c->hist); dev_free(c->tot); dev_free(c->partial); dev_free(c->ranges); dev_free(c->units); dev_free(c->far_cnt); dev_free(c->far_diff); dev_free(c->tile_failed); dev_free(c->tile_open); dev_free(c->open_sat); dev_free(c->n_units); dev_free(c->d_status); dev_free(c->d_fb); dev_free(c->d_fb_bak); dev_free(c->d_tap);
   for (int k = 0; k < 2; ++k) { dev_free(c->ikeys[k]); dev_free(c->ivals[k]); }
   if (c->h_status) cudaFreeHost(c->h_status);
+  if (c->h_ring) cudaFreeHost(c->h_ring);
+  for (int i = 0; i < splat_ctx::RING; ++i) if (c->ring_ev[i]) cudaEventDestroy(c->ring_ev[i]);
   if (c->h_wd) cudaFreeHost(c->h_wd);
   for (int i = 0; i < EV_COUNT_; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->status_ev) cudaEventDestroy(c->status_ev);
@@ -944,6 +1163,39 @@ int splat_upload_soa(splat_ctx *c, const float *pos4, const float *scale3, const
   return SPLAT_OK;
 }
 
+int splat_upload_ply_raw(splat_ctx *c, const void *vertex_rows, uint64_t n, uint32_t stride_floats, float *activated60) {
+  if (!c) return SPLAT_ERR_INVALID;
+  if (!vertex_rows) return fail(c, SPLAT_ERR_INVALID, "null vertex payload");
+  if (stride_floats < (uint32_t)PLY_FLOATS) return fail(c, SPLAT_ERR_INVALID, "the INRIA vertex layout has 62 floats per vertex");
+  if (!c->members.empty()) {
+    int rc = splat_upload_ply_raw(c->members[0], vertex_rows, n, stride_floats, activated60);
+    if (rc) { c->err = c->members[0]->err; return rc; }
+    return group_broadcast_scene(c);
+  }
+  int rc = upload_common(c, n);
+  if (rc) return rc;
+  float *raw = nullptr, *act = nullptr, *mean3 = nullptr;
+  const size_t raw_floats = (size_t)n * stride_floats, act_floats = (size_t)n * 60;
+  cudaError_t e = dev_alloc(&raw, raw_floats);
+  if (e == cudaSuccess) e = dev_alloc(&act, act_floats);
+  if (e == cudaSuccess) e = dev_alloc(&mean3, 4);
+  float *d_pos = act, *d_rot = act + 4 * n, *d_scale = act + 8 * n, *d_op = act + 11 * n, *d_sh = act + 12 * n;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(raw, vertex_rows, raw_floats * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) {
+    ply_mean_kernel<<<1, 1024, 0, c->stream>>>(raw, stride_floats, n, mean3);
+    ply_activate_kernel<<<cdiv(n, PLY_ROWS), PLY_ROWS, 0, c->stream>>>(raw, stride_floats, (uint32_t)n, mean3, reinterpret_cast<float4 *>(d_pos),
+                                                                      d_scale, d_op, reinterpret_cast<float4 *>(d_rot), d_sh);
+    pack_scene_kernel<<<cdiv(n, 256), 256, 0, c->stream>>>(reinterpret_cast<const float4 *>(d_pos), d_scale, d_op,
+                                                           reinterpret_cast<const float4 *>(d_rot), d_sh, c->scene, (uint32_t)n);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess && activated60) e = cudaMemcpyAsync(activated60, act, act_floats * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(raw); cudaFree(act); cudaFree(mean3);
+  if (e != cudaSuccess) { free_scene(c); return fail(c, e == cudaErrorMemoryAllocation ? SPLAT_ERR_NOMEM : SPLAT_ERR_CUDA, "PLY ingest", e); }
+  return SPLAT_OK;
+}
+
 int splat_upload_aos(splat_ctx *c, const float *g59, uint64_t n) {
   if (!c) return SPLAT_ERR_INVALID;
   if (!c->members.empty()) {
@@ -973,7 +1225,7 @@ static int report_skipped(splat_ctx *c) {
   poll_status(c);
   if (!c->retry_pending) return SPLAT_OK;
   c->retry_pending = false;
-  int rc = ensure_instances(c, c->last_instances + c->last_instances / 4 + 65536u);
+  int rc = ensure_instances(c, grow_target(c));
   if (rc) return rc;
   return fail(c, SPLAT_ERR_RETRY, "the previous splat_render_device frame was not rendered (its tile instances did not fit the "
                                   "buffers, which have now been grown; its target is untouched): render it again");
@@ -996,7 +1248,10 @@ int splat_render_device(splat_ctx *c, const splat_camera *cam, void *fb_rows_dev
 }
 
 // host-buffer frames: the call waits for the frame anyway, so a skipped frame is simply repeated
-static int host_frame(splat_ctx *c, const FrameParams &P, uint32_t *host_fb, size_t px, cudaEvent_t wait_ev) {
+// `restore` puts the frame's initial contents back into d_fb (on c->stream): a skipped frame blended
+// nothing if it had no near cut, but the first pass of a near-cut frame may already have written tiles.
+static int host_frame(splat_ctx *c, const FrameParams &P, uint32_t *host_fb, size_t px, cudaEvent_t wait_ev,
+                      const std::function<int()> &restore) {
   int rc = render_frame(c, P, c->d_fb, c->stream, wait_ev);
   if (rc) { cudaStreamSynchronize(c->copy_stream); return rc; }
   for (int attempt = 0;; ++attempt) {
@@ -1007,7 +1262,9 @@ static int host_frame(splat_ctx *c, const FrameParams &P, uint32_t *host_fb, siz
     if (rc) return rc;
     if (c->status_pending) absorb_status(c);
     if (!c->retry_pending || attempt >= 2) break;
-    rc = finish_frame(c);          // grows the buffers, renders the frame again (d_fb was left untouched)
+    rc = restore();
+    if (rc) return rc;
+    rc = finish_frame(c);          // grows the buffers, renders the frame again with a host round trip
     if (rc) return rc;
   }
   c->host_copy = true;
@@ -1033,15 +1290,23 @@ int splat_render_rows(splat_ctx *c, const splat_camera *cam, uint32_t *fb_rows, 
   if (px > c->fb_cap) {
     CU(cudaStreamSynchronize(c->stream));
     dev_free(c->d_fb);
+    dev_free(c->d_fb_bak);
     CU(dev_alloc(&c->d_fb, px));
+    CU(dev_alloc(&c->d_fb_bak, px));
     c->fb_cap = px;
   }
-  // upload on the copy stream: overlaps project/sort/binning, only blend waits for it
+  // upload on the copy stream: overlaps project/sort/binning, only blend waits for it; a device-side
+  // copy of the uploaded pixels is kept in case the frame has to be repeated (the host buffer is
+  // overwritten by the download)
   CU(cudaEventRecord(c->ev[EV_H2D0], c->copy_stream));
   CU(cudaMemcpyAsync(c->d_fb, fb_rows, px * 4, cudaMemcpyHostToDevice, c->copy_stream));
   CU(cudaEventRecord(c->ev[EV_H2D1], c->copy_stream));
+  CU(cudaMemcpyAsync(c->d_fb_bak, c->d_fb, px * 4, cudaMemcpyDeviceToDevice, c->copy_stream));
   CU(cudaEventRecord(c->h2d_done, c->copy_stream));
-  return host_frame(c, P, fb_rows, px, c->h2d_done);
+  return host_frame(c, P, fb_rows, px, c->h2d_done, [c, px]() -> int {
+    CU(cudaMemcpyAsync(c->d_fb, c->d_fb_bak, px * 4, cudaMemcpyDeviceToDevice, c->stream));
+    return SPLAT_OK;
+  });
 }
 
 int splat_render(splat_ctx *c, const splat_camera *cam, uint32_t *fb, uint32_t W, uint32_t H) {
@@ -1064,17 +1329,24 @@ int splat_render_cleared(splat_ctx *c, const splat_camera *cam, uint32_t *fb_out
   if (px > c->fb_cap) {
     CU(cudaStreamSynchronize(c->stream));
     dev_free(c->d_fb);
+    dev_free(c->d_fb_bak);
     CU(dev_alloc(&c->d_fb, px));
+    CU(dev_alloc(&c->d_fb_bak, px));
     c->fb_cap = px;
   }
+  auto clear_fb = [c, px, clear]() -> int {
+    if (clear == 0u || ((clear & 0xFFu) * 0x01010101u) == clear) {
+      CU(cudaMemsetAsync(c->d_fb, (int)(clear & 0xFFu), px * 4, c->stream));
+    } else {
+      fill_u32_kernel<<<cdiv(px, 1024), 256, 0, c->stream>>>(c->d_fb, clear, px);
+    }
+    return SPLAT_OK;
+  };
   CU(cudaEventRecord(c->ev[EV_H2D0], c->stream));
-  if (clear == 0u || ((clear & 0xFFu) * 0x01010101u) == clear) {
-    CU(cudaMemsetAsync(c->d_fb, (int)(clear & 0xFFu), px * 4, c->stream));
-  } else {
-    fill_u32_kernel<<<cdiv(px, 1024), 256, 0, c->stream>>>(c->d_fb, clear, px);
-  }
+  rc = clear_fb();
+  if (rc) return rc;
   CU(cudaEventRecord(c->ev[EV_H2D1], c->stream));
-  return host_frame(c, P, fb_out, px, nullptr);
+  return host_frame(c, P, fb_out, px, nullptr, clear_fb);
 }
 
 int splat_debug_render_float(splat_ctx *c, const splat_camera *cam, uint32_t *fb_inout, uint32_t W, uint32_t H, float *rgba) {
@@ -1106,7 +1378,7 @@ int splat_get_timings(splat_ctx *c, splat_timings *t) {
   if (!c->have_frame) return fail(c, SPLAT_ERR_STATE, "no frame rendered yet");
   CU(cudaSetDevice(c->cfg.device));
   if (c->status_pending) {
-    int rcw = wait_done(c, c->status_ev, c->last_stream, "frame");
+    int rcw = wait_done(c, last_status_event(c), c->last_stream, "frame");
     if (rcw) return rcw;
     absorb_status(c);
   } else {
@@ -1121,6 +1393,10 @@ int splat_get_timings(splat_ctx *c, splat_timings *t) {
   t->bin_ms = el(EV_DSORT, EV_COUNT) + el(EV_COUNT, EV_EMIT) + el(EV_TSORT, EV_RANGES);
   t->blend_ms = el(EV_RANGES, EV_BLEND);
   t->total_ms = el(EV_START, EV_BLEND);
+  if (c->last_cut) {
+    t->second_pass_ms = el(EV_BLEND, EV_B_END);
+    t->total_ms += t->second_pass_ms;
+  }
   if (c->host_copy) {
     CU(cudaEventSynchronize(c->ev[EV_D2H1]));
     t->h2d_ms = el(EV_H2D0, EV_H2D1);
@@ -1136,6 +1412,8 @@ int splat_get_timings(splat_ctx *c, splat_timings *t) {
   t->near_cut_failed = c->last_failed;
   t->near_cut_instances = c->last_cut_instances;
   t->frames_skipped = c->frames_skipped;
+  t->second_pass_instances = c->last_second_instances;
+  t->near_cut_fallbacks = c->near_cut_fallbacks;
   return SPLAT_OK;
 }
 
@@ -1146,7 +1424,7 @@ int splat_get_tile_loads(splat_ctx *c, uint32_t *per_tile, uint64_t cap, uint64_
   if (!c->loads_valid) return fail(c, SPLAT_ERR_STATE, "the last frame's second pass binned only part of the screen (near cut): no complete tile lists");
   CU(cudaSetDevice(c->cfg.device));
   { int rcw = wait_done(c, c->ev[EV_BLEND], c->last_stream, "frame"); if (rcw) return rcw; }
-  if (c->status_pending && cudaEventQuery(c->status_ev) == cudaSuccess) absorb_status(c);
+  poll_status(c);
   const uint64_t T = c->last_tiles, m = std::min<uint64_t>(cap, T);
   *n_tiles = T;
   if (c->last_instances == 0) { std::memset(per_tile, 0, m * sizeof(uint32_t)); return SPLAT_OK; }
@@ -1215,6 +1493,20 @@ int splat_debug_sort_pairs(splat_ctx *c, uint32_t *keys, uint32_t *vals, uint64_
   for (int i = 0; i < 2; ++i) { dev_free(k[i]); dev_free(v[i]); }
   c->n = saved_n;
   return rc;
+}
+
+int splat_debug_read_tiles(splat_ctx *c, int which, uint32_t *out, uint64_t cap_words, uint64_t *n_words) {
+  // tests / diagnostics: per-tile arrays of the last frame.  which: 0 = list ranges (2 words per tile),
+  // 1 = far_cnt (cut Gaussians per tile), 2 = tile_failed
+  if (!c || !out || !n_words || which < 0 || which > 2) return SPLAT_ERR_INVALID;
+  if (!c->have_frame || !c->members.empty()) return fail(c, SPLAT_ERR_STATE, "no frame rendered yet");
+  CU(cudaSetDevice(c->cfg.device));
+  CU(cudaDeviceSynchronize());
+  const uint64_t T = c->last_tiles, words = which == 0 ? 2 * T : T;
+  *n_words = words;
+  const void *src = which == 0 ? (const void *)c->ranges : (which == 1 ? (const void *)c->far_cnt : (const void *)c->tile_failed);
+  CU(cudaMemcpy(out, src, std::min(cap_words, words) * 4u, cudaMemcpyDeviceToHost));
+  return SPLAT_OK;
 }
 
 int splat_debug_blend_stats(splat_ctx *c, uint64_t *out8, int reset) {

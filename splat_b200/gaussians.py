@@ -279,6 +279,33 @@ def load_ply_soa(filename: str) -> GaussianList:
     return GaussianList(pos, scales, opac, rot, sh)
 
 
+def ply_vertex_payload(filename: str):
+    """(rows, n): the vertex payload of a binary_little_endian PLY in the INRIA 3DGS layout as an
+    (n, 62) float32 memory map of the file -- what `splat_upload_ply_raw` takes.  Raises when the file
+    has another element, property order or format (use load_ply_soa for those)."""
+    with open(filename, "rb") as f:
+        head = f.read(1 << 16)
+    end = head.index(b"end_header\n") + len(b"end_header\n")
+    lines = head[:end].decode("ascii").split("\n")
+    n, props, fmt = 0, [], None
+    for ln in lines[1:]:
+        t = ln.split()
+        if not t:
+            continue
+        if t[0] == "format":
+            fmt = t[1]
+        elif t[0] == "element":
+            if t[1] != "vertex":
+                raise ValueError("Unexpected element!")
+            n = int(t[2])
+        elif t[0] == "property":
+            props.append((t[2], t[1]))
+    if fmt != "binary_little_endian" or [p for p, _ in props] != _PLY_PROPS or any(ty not in ("float", "float32") for _, ty in props):
+        raise ValueError("not the INRIA 62-float binary_little_endian vertex layout")
+    rows = np.memmap(filename, dtype="<f4", mode="r", offset=end, shape=(n, len(_PLY_PROPS)))
+    return rows, n
+
+
 def trim_ply(src: str, dst: str, count: int = 3) -> int:
     """`trim` (src/bin/00_ply_load.rs:9-63): copy the first `count` vertices of a binary
     little-endian PLY into a new PLY with the same header otherwise (tiny test scenes).  Returns

@@ -84,6 +84,19 @@ def _min_max_partition(w: np.ndarray, parts: int) -> List[int]:
     return cuts
 
 
+def rebalance(bounds: Bounds, times_ms: Sequence[float], H: int) -> Bounds:
+    """New stripe boundaries from the ranks' measured frame times (the same rule as the library's
+    group contexts, splat_api.cu rebalance_bounds): the cost of a tile row is taken as uniform inside
+    the stripe that rendered it, and the rows are re-cut with the min-max partition."""
+    tr = tile_rows(H)
+    w = np.zeros(tr, np.float64)
+    for (r0, r1), t in zip(bounds, times_ms):
+        t0, t1 = r0 // TILE, (r1 + TILE - 1) // TILE
+        if t1 > t0:
+            w[t0:t1] = max(float(t), 1e-4) / (t1 - t0)
+    return stripe_bounds(H, len(bounds), w)
+
+
 def stripe_cuts_equal(n: int, parts: int) -> List[int]:
     base, rem = divmod(n, parts)
     cuts, r = [0], 0

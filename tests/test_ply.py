@@ -82,3 +82,59 @@ def test_trim_keeps_the_first_vertices(tmp_path):
     # activations are per vertex; only the recentring (mean over the file) differs
     assert np.array_equal(a.scales[:3], b.scales[:3]) and np.array_equal(a.sh[:3], b.sh[:3])
     assert np.array_equal(a.opacities[:3], b.opacities[:3]) and np.array_equal(a.rotations[:3], b.rotations[:3])
+
+
+# --------------------------------------------------------------------------- device ingest (f-1)
+@pytest.mark.gpu
+def test_device_ply_ingest_matches_host_loader_and_renders_identically(tmp_path):
+    """splat_upload_ply_raw: the raw vertex payload is activated ON THE DEVICE (exp / sigmoid /
+    rot_0 -> w / f_rest_i -> sh[3+i]) and recentred with the reference's sequential f32 mean
+    (gaussians.rs:258-282, :394-402).  Against the numpy host loader: positions, rotations and SH
+    are bit-identical; scales and opacities agree to two ulps (the device uses the library's pinned
+    exp, numpy its own -- neither is Rust's libm, include/splat.h says so).  Uploading the activated
+    arrays through splat_upload_soa renders the same frame, which equals the oracle's."""
+    from oracle import oracle as orc
+    from splat_b200 import _lib
+    from splat_b200.camera import Camera
+    from splat_b200.gaussians import load_ply_soa, save_ply
+
+    orc.build()
+    rng = np.random.default_rng(11)
+    n = 20_000
+    raw = {"x": rng.normal(2.0, 1.0, n), "y": rng.normal(-1.0, 0.7, n), "z": rng.normal(0.5, 1.2, n),
+           "opacity": rng.normal(0.5, 2.0, n), "rot_0": rng.normal(size=n), "rot_1": rng.normal(size=n),
+           "rot_2": rng.normal(size=n), "rot_3": rng.normal(size=n)}
+    for i in range(3):
+        raw[f"scale_{i}"] = rng.normal(-3.2, 0.7, n)
+        raw[f"f_dc_{i}"] = rng.normal(0.0, 1.2, n)
+    for i in range(45):
+        raw[f"f_rest_{i}"] = rng.normal(0.0, 0.15, n)
+    path = str(tmp_path / "scene.ply")
+    save_ply(path, raw)
+    host = load_ply_soa(path)
+
+    ctx = _lib.Context(device=0)
+    dev = ctx.upload_ply(path, want_activated=True)
+    assert np.array_equal(dev.positions, host.positions)          # incl. the sequential-f32 mean
+    assert np.array_equal(dev.rotations, host.rotations) and np.array_equal(dev.sh, host.sh)
+
+    def ulps(a, b):
+        return np.abs(a.view(np.int32).astype(np.int64) - b.view(np.int32).astype(np.int64)).max()
+
+    assert ulps(dev.scales, host.scales) <= 2 and np.allclose(dev.opacities, host.opacities, rtol=1e-6, atol=0)
+    W, H = 400, 300
+    cam = Camera(H, W, (0.0, 0.0, 4.0))
+    cam.update_camera_pose()
+    cs = _lib.camera_struct(cam)
+    a = np.zeros((H, W), np.uint32)
+    ctx.render(cs, a)
+    ctx2 = _lib.Context(device=0)
+    ctx2.upload(dev)
+    b = np.zeros((H, W), np.uint32)
+    ctx2.render(cs, b)
+    ref = np.zeros((H, W), np.uint32)
+    orc.render(dev, orc.camera_from(cam), orc.make_config(), ref)
+    assert np.count_nonzero(ref) > W * H // 10
+    assert np.array_equal(a, b) and np.array_equal(a, ref)
+    ctx.close()
+    ctx2.close()

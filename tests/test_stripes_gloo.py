@@ -133,3 +133,33 @@ def test_world_size_2_gather_equals_full_frame(balanced):
         assert p.exitcode == 0
     assert ok, f"{bad} pixels differ after the gather (bounds {bounds})"
     assert bounds[0][1] == bounds[1][0] and bounds[1][1] == 150
+
+
+def test_rebalance_from_measured_times_moves_rows_to_the_fast_ranks():
+    """stripes.rebalance: the cost of a tile row is taken as uniform inside the stripe that rendered
+    it; re-cutting gives the slow rank fewer rows, keeps the cover tile aligned and gap free, and is a
+    fixed point when all ranks take the same time."""
+    from splat_b200 import stripes
+
+    H = 1080
+    b0 = stripes.stripe_bounds(H, 4)
+    same = stripes.rebalance(b0, [1.0, 1.0, 1.0, 1.0], H)
+    stripes.check_bounds(same, H)
+    rows = lambda b: [r1 - r0 for r0, r1 in b]
+    assert max(rows(same)) - min(rows(same)) <= 16 * 2
+    b1 = stripes.rebalance(b0, [0.5, 2.0, 2.0, 0.5], H)      # the two centre stripes are 4x as slow
+    stripes.check_bounds(b1, H)
+    assert rows(b1)[1] < rows(b0)[1] and rows(b1)[2] < rows(b0)[2]
+    assert rows(b1)[0] > rows(b0)[0] and rows(b1)[3] > rows(b0)[3]
+    # predicted times under the uniform-within-stripe model are closer together than before
+    def predict(bounds, old_bounds, t):
+        dens = np.zeros((H + 15) // 16)
+        for (r0, r1), tt in zip(old_bounds, t):
+            t0, t1 = r0 // 16, (r1 + 15) // 16
+            dens[t0:t1] = tt / max(t1 - t0, 1)
+        return [dens[r0 // 16:(r1 + 15) // 16].sum() for r0, r1 in bounds]
+    p = predict(b1, b0, [0.5, 2.0, 2.0, 0.5])
+    assert max(p) < 2.0 * 0.8 and max(p) / min(p) < 1.35
+    # an empty stripe in the input (more ranks than work) is tolerated
+    b2 = stripes.rebalance([(0, 0), (0, 544), (544, 1080)], [0.0, 1.0, 1.0], H)
+    stripes.check_bounds(b2, H)
