@@ -215,7 +215,8 @@ def workload_config(args):
 def parallelism(args, world):
     return (f"screen-tile stripes x{world}, " + ("equal" if args.equal_stripes else "cut from a probe frame, re-cut from measured per-rank times")
             + ", scene broadcast once (splat_comm_broadcast_scene), one grouped ncclSend/ncclRecv gather per frame "
-              "(splat_gather_stripes)") if world > 1 else "single GPU"
+              "(splat_gather_stripes), stripe frames " + ("without host waits" if args.stripe_mode == "async" else "with one host round trip each")
+            ) if world > 1 else "single GPU"
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -248,7 +249,14 @@ def run_ours(args):
     # ---- scene: generated and uploaded on rank 0, then broadcast once inside the library (C0:
     # ncclBroadcast of the packed device scene over the context's own communicator)
     from splat_b200 import stripes
-    ctx = _lib.Context(device=local, lowpass=LOWPASS, near_cut=args.near_cut)
+    # N > 1: by default every stripe frame reads its tile-instance count on the host (sync_frames = 1, no near
+    # cut): such a frame can never be abandoned on the device, so no rank ever has to repeat a frame while its
+    # peers sit in the gather.  --stripe-mode async enqueues stripes without host waits (measured at 2 GPUs and
+    # at 4K x 8; at 1080p x 8 the narrow stripes outgrew their launch bounds and an unhandled retry in this
+    # harness hung the round-2 run -- handled below since, but not re-measured: see BASELINE.md).
+    stripe_async = world > 1 and args.stripe_mode == "async"
+    ctx = _lib.Context(device=local, lowpass=LOWPASS, near_cut=args.near_cut if (world == 1 or stripe_async) else 0,
+                       sync_frames=1 if (world > 1 and not stripe_async) else 0)
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:
@@ -305,24 +313,38 @@ def run_ours(args):
         fb_dev[r0:r1].zero_()                          # main.rs:73 clear
         ctx.render_device(cam_structs[i], fb_dev[r0:r1].data_ptr(), W, H, r0, r1, stream.cuda_stream)
 
+    def stripe_with_retry(i):
+        """this rank's stripe of frame i.  SPLAT_ERR_RETRY (the previous frame outgrew its launch bound or its near
+        lists and was abandoned on the device; the library has grown its buffers) is handled HERE, with local work
+        only -- never with a collective -- so that every rank still issues exactly one gather per frame."""
+        for attempt in range(6):
+            try:
+                render_stripe(i)
+                return
+            except _lib.SplatError as e:
+                if e.code != -6 or attempt == 5:
+                    raise
+                repeats[0] += 1
+                try:                                   # the abandoned frame's work belongs to the timed region too
+                    render_stripe(max(i - 1, 0))
+                except _lib.SplatError as e2:
+                    if e2.code != -6:
+                        raise
+
+    def stripe_timings(i):
+        """stage times of this rank's stripe of frame i (waits for it); an abandoned frame is rendered again, locally"""
+        for attempt in range(6):
+            try:
+                return ctx.timings()
+            except _lib.SplatError as e:
+                if e.code != -6 or attempt == 5:
+                    raise
+                repeats[0] += 1
+                stripe_with_retry(i)
+
     def frame_device(i):
         if r1 > r0:
-            for attempt in range(4):
-                try:
-                    render_stripe(i)
-                    break
-                except _lib.SplatError as e:
-                    # SPLAT_ERR_RETRY: the previous frame's tile instances outgrew the launch bound (+12.5% per
-                    # frame) and it was abandoned on the device; the library has grown its buffers.  Render that
-                    # frame again, then this one (all of it inside the timed region).
-                    if e.code != -6 or attempt == 3:
-                        raise
-                    repeats[0] += 1
-                    try:
-                        render_stripe(max(i - 1, 0))
-                    except _lib.SplatError as e2:
-                        if e2.code != -6:
-                            raise
+            stripe_with_retry(i)
         gather_frame()
 
     def sync_all():
@@ -338,7 +360,7 @@ def run_ours(args):
             for i in range(4):
                 frame_device(i)
                 if r1 > r0 and i >= 1:
-                    tsum += ctx.timings()["total_ms"]
+                    tsum += stripe_timings(i)["total_ms"]
             sync_all()
             tt = torch.tensor([tsum / 3.0], device=dev, dtype=torch.float64)
             allt = [torch.zeros_like(tt) for _ in range(world)]
@@ -376,15 +398,7 @@ def run_ours(args):
     for i in range(Wm, Wm + K):
         frame_device(i)
         if r1 > r0:
-            for attempt in range(4):
-                try:
-                    tm = ctx.timings()
-                    break
-                except _lib.SplatError as e:       # this very frame was abandoned on the device: render it again
-                    if e.code != -6 or attempt == 3:
-                        raise
-                    repeats[0] += 1
-                    frame_device(i)
+            tm = stripe_timings(i)
             for k_ in stage:
                 stage[k_] += tm[k_]
             inst_sum += tm["n_instances"]
@@ -565,6 +579,9 @@ def main():
     ap.add_argument("--near-cut", type=int, default=-1,
                     help="splat_config.near_cut: -1 = automatic (the library default), 0 = off, 1..1024 = fixed fraction")
     ap.add_argument("--equal-stripes", action="store_true", help="N > 1: equal tile-row stripes instead of load-balanced ones")
+    ap.add_argument("--stripe-mode", default="sync", choices=["sync", "async"],
+                    help="N > 1: 'sync' (default) reads the tile-instance count on the host in every stripe frame, so no frame "
+                         "can be abandoned on the device; 'async' enqueues stripes without any host wait (and with the near cut)")
     ap.add_argument("--rebalance-rounds", type=int, default=4, help="N > 1: stripe re-cuts from measured per-rank times before the warm-up")
     args = ap.parse_args()
     capture_stdout()

@@ -210,7 +210,8 @@ __global__ void __launch_bounds__(256)
 project_kernel(const float4 *__restrict__ scene, const __grid_constant__ FrameParams P,
                Rec *__restrict__ recs, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
                uint2 *__restrict__ rects, uint32_t *__restrict__ tcnt,
-               const uint32_t *__restrict__ surv, const uint32_t *__restrict__ n_surv) {
+               const uint32_t *__restrict__ surv, const uint32_t *__restrict__ n_surv,
+               uint32_t *__restrict__ block_kept /* !SURV stripe frames: kept Gaussians per CTA (compact_pairs_kernel) */) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t n = P.n;
   const uint32_t count = SURV ? *n_surv : n;
@@ -345,6 +346,36 @@ project_kernel(const float4 *__restrict__ scene, const __grid_constant__ FramePa
     vals[j] = i;
     rects[i] = make_uint2((uint32_t)tr.x0 | ((uint32_t)tr.y0 << 16), (uint32_t)tr.x1 | ((uint32_t)tr.y1 << 16));
     tcnt[i] = tr.count();   // 4-byte gather target for tile_count_kernel (8 per sector, stays in L2)
+  }
+  if (!SURV && block_kept) {
+    const int kept = __syncthreads_count(valid && vis);
+    if (threadIdx.x == 0) block_kept[blockIdx.x] = (uint32_t)kept;
+  }
+}
+
+// Dense stripes (most Gaussians can reach the stripe: the pre-pass would only add work): the full
+// projection ran over all Gaussians; squeeze the (depth key, index) pairs of the kept ones to the
+// front, in index order (the stable sort's tie-break is the input order).  CTA b owns the 256 pairs
+// project_kernel's CTA b wrote; block_off = exclusive scan of block_kept.
+__global__ void __launch_bounds__(256)
+compact_pairs_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                     uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
+                     const uint32_t *__restrict__ block_off, uint32_t n) {
+  __shared__ uint32_t wcnt[8];
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x, lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  uint32_t k = KEY_CULLED, v = 0;
+  if (i < n) { k = keys_in[i]; v = vals_in[i]; }
+  const bool keep = k != KEY_CULLED;
+  const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
+  if (lane == 0) wcnt[w] = __popc(bal);
+  __syncthreads();
+  uint32_t before = 0;
+#pragma unroll
+  for (uint32_t q = 0; q < 8u; ++q) before += (q < w) ? wcnt[q] : 0u;
+  if (keep) {
+    const uint32_t o = block_off[blockIdx.x] + before + __popc(bal & ((1u << lane) - 1u));
+    keys_out[o] = k;
+    vals_out[o] = v;
   }
 }
 

@@ -696,9 +696,26 @@ int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cuda
   CU(cudaEventRecord(c->ev[EV_START], s));
   CU(cudaMemsetAsync(c->d_status, 0, offsetof(FrameStatus, skipped), s));
   const uint32_t *n_sorted = nullptr;
+  int cur0 = 0;                 // which keys[] / vals[] buffer holds the pairs that enter the depth sort
+  bool dense_stripe = false;
   if (!P.stripe_cull) {
-    project_kernel<false><<<cdiv(n, 256), 256, 0, s>>>(c->scene, P, c->recs, c->keys[0], c->vals[0], c->rects, c->tcnt, nullptr, nullptr);
+    project_kernel<false><<<cdiv(n, 256), 256, 0, s>>>(c->scene, P, c->recs, c->keys[0], c->vals[0], c->rects, c->tcnt, nullptr, nullptr, nullptr);
     LAUNCHED("project_kernel");
+  } else if (async && c->last_sort * 10u > (uint64_t)n * 3u) {
+    // Dense stripe (the last frame kept more than 30% of the Gaussians: with 16-byte planes nearly every
+    // sector would be read anyway and the pre-pass only adds work): full projection over all Gaussians,
+    // those that cannot reach the stripe culled inside, then the kept pairs squeezed to the front.
+    const uint32_t nb = cdiv(n, 256), np = std::max(1u, cdiv(nb, SC_BLOCK));
+    project_kernel<false><<<nb, 256, 0, s>>>(c->scene, P, c->recs, c->keys[0], c->vals[0], c->rects, c->tcnt, nullptr, nullptr, c->block_kept);
+    scan_reduce_kernel<<<np, SC_THREADS, 0, s>>>(c->block_kept, c->partial, nb);
+    scan_partials_kernel<<<1, 1024, 0, s>>>(c->partial, np, &c->d_status->n_sort);
+    scan_apply_kernel<<<np, SC_THREADS, 0, s>>>(c->block_kept, c->block_kept, c->partial, nb);
+    compact_pairs_kernel<<<nb, 256, 0, s>>>(c->keys[0], c->vals[0], c->keys[1], c->vals[1], c->block_kept, n);
+    n_sorted = reinterpret_cast<const uint32_t *>(&c->d_status->n_sort);
+    cur0 = 1;
+    dense_stripe = true;
+    c->launches += 4;
+    LAUNCHED("project_kernel + pair compaction (dense stripe)");
   } else {
     // Stripe (multi-GPU) frames: a 48 B/Gaussian pre-pass votes which Gaussians can reach the rows
     // of this stripe; the survivors' indices are compacted in index order and the projection runs
@@ -714,14 +731,14 @@ int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cuda
     compact_idx_kernel<<<nb, 256, 0, s>>>(mask, c->block_kept, surv, n);
     n_sorted = reinterpret_cast<const uint32_t *>(&c->d_status->n_sort);   // low word (n < 2^31)
     project_kernel<true><<<std::max(1u, cdiv(sort_bound, 256)), 256, 0, s>>>(c->scene, P, c->recs, c->keys[0], c->vals[0], c->rects, c->tcnt,
-                                                                          surv, n_sorted);
+                                                                          surv, n_sorted, nullptr);
     c->launches += 5;
     LAUNCHED("stripe pre-pass + project_kernel");
   }
   CU(cudaEventRecord(c->ev[EV_PROJECT], s));
-  int cur = 0;
+  int cur = cur0;
   // (a stripe sorts only its survivors -- a device-side count; the CTAs beyond it exit at once)
-  cur = radix_sort(c, s, c->keys, c->vals, P.stripe_cull ? sort_bound_all(c, P, async, n) : n, 32, cur, n_sorted, n);
+  cur = radix_sort(c, s, c->keys, c->vals, (P.stripe_cull && !dense_stripe) ? sort_bound_all(c, P, async, n) : n, 32, cur, n_sorted, n);
   if (cur < 0) return cur;
   c->order_buf = cur;
   CU(cudaEventRecord(c->ev[EV_DSORT], s));
@@ -1446,7 +1463,7 @@ int splat_debug_project(splat_ctx *c, const splat_camera *cam, uint32_t W, uint3
   if (rc) return rc;
   CU(cudaSetDevice(c->cfg.device));
   CU(cudaMemsetAsync(c->recs, 0, (size_t)c->n * sizeof(Rec), c->stream));
-  project_kernel<false><<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->scene, P, c->recs, c->keys[0], c->vals[0], c->rects, c->tcnt, nullptr, nullptr);
+  project_kernel<false><<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->scene, P, c->recs, c->keys[0], c->vals[0], c->rects, c->tcnt, nullptr, nullptr, nullptr);
   CU(cudaGetLastError());
   if (records12) CU(cudaMemcpyAsync(records12, c->recs, (size_t)c->n * sizeof(Rec), cudaMemcpyDeviceToHost, c->stream));
   if (depth_keys) CU(cudaMemcpyAsync(depth_keys, c->keys[0], (size_t)c->n * 4, cudaMemcpyDeviceToHost, c->stream));
