@@ -309,8 +309,13 @@ def run_ours(args):
 
     repeats = [0]
 
+    upload_from = [None]      # e2e frames: the pinned host rows this rank uploads instead of clearing on the device
+
     def render_stripe(i):
-        fb_dev[r0:r1].zero_()                          # main.rs:73 clear
+        if upload_from[0] is None:
+            fb_dev[r0:r1].zero_()                      # main.rs:73 clear
+        else:
+            fb_dev[r0:r1].copy_(upload_from[0][: r1 - r0], non_blocking=True)      # H2D of this rank's (cleared) stripe
         ctx.render_device(cam_structs[i], fb_dev[r0:r1].data_ptr(), W, H, r0, r1, stream.cuda_stream)
 
     def stripe_with_retry(i):
@@ -369,7 +374,8 @@ def run_ours(args):
             new_bounds = stripes.rebalance(bounds, times, H)
             if rank == 0:
                 log(f"[bench] rebalance {it}: per-rank ms " + " ".join(f"{t:.3f}" for t in times) + f" -> {new_bounds}")
-            if new_bounds == bounds or max(times) < 1.08 * min(t for t in times if t > 0):
+            busy = [t for t in times if t > 0]
+            if new_bounds == bounds or not busy or max(times) < 1.08 * min(busy):
                 break
             bounds = new_bounds
             stripes.check_bounds(bounds, H)
@@ -386,6 +392,7 @@ def run_ours(args):
     stage = {"project_ms": 0.0, "sort_ms": 0.0, "bin_ms": 0.0, "blend_ms": 0.0, "second_pass_ms": 0.0, "total_ms": 0.0}
     second_sum = 0
     inst_sum, launches, cut_sum, fallbacks = 0, 0, 0, 0
+    tm_last = {}
     ev0.record(stream)
     for i in range(Wm, Wm + K):
         frame_device(i)                                 # no per-frame host wait beyond the call's own
@@ -406,6 +413,7 @@ def run_ours(args):
             second_sum += tm["second_pass_instances"]
             fallbacks += 1 if tm["near_cut_failed"] else 0
             launches += tm["kernel_launches"] + 1       # + the clear
+            tm_last = tm
     sync_all()
     if world > 1:
         log(f"[bench] rank {rank}: rows [{r0},{r1}) stage ms/frame " + ", ".join(f"{k_[:-3]} {v / K:.3f}" for k_, v in stage.items())
@@ -430,8 +438,11 @@ def run_ours(args):
         else:
             if r1 > r0:
                 my_host.zero_()
-                fb_dev[r0:r1].copy_(my_host[: r1 - r0], non_blocking=True)          # H2D of this rank's stripe
-                ctx.render_device(cam_structs[i], fb_dev[r0:r1].data_ptr(), W, H, r0, r1, stream.cuda_stream)
+                upload_from[0] = my_host
+                try:
+                    stripe_with_retry(i)
+                finally:
+                    upload_from[0] = None
             gather_frame()
             if rank == 0:
                 host_fb.copy_(fb_dev, non_blocking=True)                             # D2H of the gathered frame
@@ -507,7 +518,7 @@ def run_ours(args):
             {"value": e2e_cleared, "unit": "frames/s", "h2d_bytes_per_step": 184, "d2h_bytes_per_step": W * H * 4 + 16,
              "call": "splat_render_cleared (device-side clear instead of a host fill + upload)"},
             "gpu_launches": int(lsum.item()),
-            "frames_repeated": repeats[0],
+            "frames_repeated": repeats[0], "frames_skipped_on_device": int(tm_last.get("frames_skipped", 0)),
             "roofline": {"kernel": "blend_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": blend_ms,

@@ -81,3 +81,22 @@ def test_matrices_are_float32_and_marshal_column_major():
     assert v.dtype == np.float32
     assert np.array_equal(np.array(s.view[:]).reshape(4, 4).T.astype(np.float32), v)   # nalgebra storage
     assert s.w == 640.0 and s.h == 480.0 and np.isclose(s.focal, 240.0)
+
+
+def test_camera_matrices_match_the_executed_prototype():
+    """The view / projection matrices and the focal triple of the host mirror against the ones the
+    reference's Python prototype produced (notes/util.py Camera with PyGLM semantics, executed by
+    tools/make_golden_from_notebook.py): same look_at_rh, perspective_rh_no, constants."""
+    import json
+    import os
+
+    from conftest import GOLDEN
+
+    doc = json.load(open(os.path.join(GOLDEN, "notebook_projection.json")))
+    assert len(doc["cases"]) >= 4
+    for case in doc["cases"]:
+        cam = Camera(case["h"], case["w"], tuple(case["cam_pos"]))
+        cam.update_camera_pose()
+        assert np.allclose(cam.get_view_matrix(), np.array(case["view"]), atol=2e-6), case["name"]
+        assert np.allclose(cam.get_project_matrix(), np.array(case["proj"]), rtol=1e-6, atol=1e-6), case["name"]
+        assert np.allclose(cam.get_htanfovxy_focal(), case["htanfovxy_focal"], rtol=1e-6), case["name"]

@@ -148,4 +148,4 @@ def test_glibc_exp_variant_bounds_the_pinned_exp(orc):
     d = ch(a) - ch(b)
     assert np.abs(d).max() <= 1
     rmse = np.sqrt((d.astype(np.float64) ** 2).mean()) / 255.0
-    assert rmse < 5e-4, rmse
+    assert rmse < 1e-4, rmse        # the north-star bar (measured: 0 .. 1.6e-5)
