@@ -318,34 +318,19 @@ def run_ours(args):
             fb_dev[r0:r1].copy_(upload_from[0][: r1 - r0], non_blocking=True)      # H2D of this rank's (cleared) stripe
         ctx.render_device(cam_structs[i], fb_dev[r0:r1].data_ptr(), W, H, r0, r1, stream.cuda_stream)
 
+    def is_retry(e):
+        return isinstance(e, _lib.SplatError) and e.code == stripes.RETRY
+
     def stripe_with_retry(i):
-        """this rank's stripe of frame i.  SPLAT_ERR_RETRY (the previous frame outgrew its launch bound or its near
-        lists and was abandoned on the device; the library has grown its buffers) is handled HERE, with local work
-        only -- never with a collective -- so that every rank still issues exactly one gather per frame."""
-        for attempt in range(6):
-            try:
-                render_stripe(i)
-                return
-            except _lib.SplatError as e:
-                if e.code != -6 or attempt == 5:
-                    raise
-                repeats[0] += 1
-                try:                                   # the abandoned frame's work belongs to the timed region too
-                    render_stripe(max(i - 1, 0))
-                except _lib.SplatError as e2:
-                    if e2.code != -6:
-                        raise
+        """this rank's stripe of frame i; an abandoned previous frame is repeated with local work only, so that
+        every rank still issues exactly one gather per frame (splat_b200/stripes.py: render_with_retry)"""
+        repeats[0] += stripes.render_with_retry(render_stripe, i, is_retry)
 
     def stripe_timings(i):
-        """stage times of this rank's stripe of frame i (waits for it); an abandoned frame is rendered again, locally"""
-        for attempt in range(6):
-            try:
-                return ctx.timings()
-            except _lib.SplatError as e:
-                if e.code != -6 or attempt == 5:
-                    raise
-                repeats[0] += 1
-                stripe_with_retry(i)
+        """stage times of this rank's stripe of frame i (waits for it)"""
+        tm, rep = stripes.timings_with_retry(ctx.timings, render_stripe, i, is_retry)
+        repeats[0] += rep
+        return tm
 
     def frame_device(i):
         if r1 > r0:
@@ -567,6 +552,24 @@ def run_ours(args):
                            f"({c['raster_s']:.2f}s); wall time, nothing extrapolated; C restatement of the reference (oracle/), "
                            "not the Rust/euc binary"),
                 "pairs_per_frame": int(c["pairs_in_rect"])}
+            # how far is the pinned exp from the platform libm Rust would call?  the same frame's every 8th tile
+            # stripe once more on the CPU with glibc expf (oracle exp_mode = 1), against the pinned-exp rows
+            try:
+                cam_o = orc.camera_from(_CamView(cams_all[Wm]))
+                sp = orc.project(sc, cam_o, orc.make_config(lowpass=LOWPASS, nthreads=cores), W, H, cov3d=cov3d)
+                order = orc.sort_visible(sp)
+                trows = (H + TILE - 1) // TILE
+                vrows = np.concatenate([np.arange(t * TILE, min((t + 1) * TILE, H)) for t in range(0, trows, 8)])
+                fbv = np.zeros((H, W), np.uint32)
+                orc.rasterize_rows(sp, order, orc.make_config(lowpass=LOWPASS, nthreads=cores, exp_mode=1), fbv, vrows)
+                va, vb = c["fb"][vrows], fbv[vrows]
+                line["exp_variant"] = {
+                    "rows": int(len(vrows)), "pixels": int(va.size), "pixels_differing": int((va != vb).sum()),
+                    "rmse": max(float(np.sqrt(np.mean((chan(va, sh) - chan(vb, sh)) ** 2))) for sh in (0, 8, 16)),
+                    "note": "CPU restatement with glibc expf vs with the pinned exp the GPU path uses: the distance between two "
+                            "correct libms, which is all that separates the pinned exp from the exp Rust would call"}
+            except Exception as e:   # noqa: BLE001  (a diagnostic; never fail the bench line for it)
+                line["exp_variant"] = {"error": repr(e)}
             log(f"[bench] parity vs oracle: {line['parity']['mismatching_pixels']} of {a.size} pixels differ; CPU frame {c['frame_s']:.2f}s")
         emit(line)
     ctx.close()

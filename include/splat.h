@@ -11,6 +11,15 @@
  * (gaussians.rs:114-161, :473-522), eval_spherical_harmonics (:41-99), compute_cov3d
  * (:101-113, :446-462), and the euc 0.6.0 rasteriser loop itself (Cargo.lock:221-229).
  *
+ * PARITY is to the CPU restatement of that path in oracle/ (the reference itself cannot be built
+ * here: no Rust toolchain, euc un-vendored): bit-identical pixels for SPLAT_BLEND_REFERENCE.  Known
+ * distances from the real Rust/euc binary: (1) exp -- Rust calls the platform libm, this library one
+ * pinned operation sequence within 1 ulp of glibc's expf (about 1 pixel in 64,000 differs by one
+ * step); (2) euc's per-pixel coverage and attribute interpolation are modelled (inclusive
+ * axis-aligned quad, sampled at pixel centres, d = sample - centre), not reproduced from source;
+ * (3) Gaussians with a singular 2-D covariance or non-finite values are skipped where the reference
+ * panics or blends NaN.  Orientation (NDC +y = top row) is pinned to the reference's own images.
+ *
  * Plain C: opaque context, plain pointers and sizes, int error codes; nothing throws or aborts
  * across this boundary.  The Rust side binds it with bindgen; tests and
  * bench.py bind it with ctypes (splat_b200/_lib.py).

@@ -701,7 +701,7 @@ int render_frame(splat_ctx *c, const FrameParams &P, uint32_t *fb_rows_dev, cuda
   if (!P.stripe_cull) {
     project_kernel<false><<<cdiv(n, 256), 256, 0, s>>>(c->scene, P, c->recs, c->keys[0], c->vals[0], c->rects, c->tcnt, nullptr, nullptr, nullptr);
     LAUNCHED("project_kernel");
-  } else if (async && c->last_sort * 10u > (uint64_t)n * 3u) {
+  } else if (same_geom && !force_sync && c->last_sort * 10u > (uint64_t)n * 3u) {
     // Dense stripe (the last frame kept more than 30% of the Gaussians: with 16-byte planes nearly every
     // sector would be read anyway and the pre-pass only adds work): full projection over all Gaussians,
     // those that cannot reach the stripe culled inside, then the kept pairs squeezed to the front.

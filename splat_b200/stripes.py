@@ -97,6 +97,48 @@ def rebalance(bounds: Bounds, times_ms: Sequence[float], H: int) -> Bounds:
     return stripe_bounds(H, len(bounds), w)
 
 
+RETRY = -6   # SPLAT_ERR_RETRY (include/splat.h)
+
+
+def render_with_retry(render, i: int, is_retry, max_attempts: int = 6) -> int:
+    """One rank's stripe of frame i on the no-host-wait path.  `render(k)` enqueues frame k and may
+    raise an error for which `is_retry(err)` is true: the library then says that the PREVIOUS frame
+    was abandoned on the device (it outgrew its launch bounds or its near lists) and has grown its
+    buffers.  That is handled here with LOCAL work only -- render the abandoned frame again, then
+    frame i -- never with a collective, so that every rank still issues exactly one gather per frame
+    whatever happened to it (round 2: an unhandled retry on one rank left seven others waiting in the
+    gather).  Returns the number of frames that had to be repeated."""
+    repeated = 0
+    for attempt in range(max_attempts):
+        try:
+            render(i)
+            return repeated
+        except Exception as e:   # noqa: BLE001
+            if not is_retry(e) or attempt == max_attempts - 1:
+                raise
+            repeated += 1
+            try:
+                render(max(i - 1, 0))
+            except Exception as e2:   # noqa: BLE001
+                if not is_retry(e2):
+                    raise
+    return repeated
+
+
+def timings_with_retry(timings, render, i: int, is_retry, max_attempts: int = 6):
+    """Stage times of this rank's stripe of frame i (`timings()` waits for it).  If that very frame was
+    abandoned on the device it is rendered again, locally.  Returns (timings, frames repeated)."""
+    repeated = 0
+    for attempt in range(max_attempts):
+        try:
+            return timings(), repeated
+        except Exception as e:   # noqa: BLE001
+            if not is_retry(e) or attempt == max_attempts - 1:
+                raise
+            repeated += 1 + render_with_retry(render, i, is_retry, max_attempts)
+    raise AssertionError("unreachable")
+
+
 def stripe_cuts_equal(n: int, parts: int) -> List[int]:
     base, rem = divmod(n, parts)
     cuts, r = [0], 0

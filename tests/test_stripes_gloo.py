@@ -163,3 +163,55 @@ def test_rebalance_from_measured_times_moves_rows_to_the_fast_ranks():
     # an empty stripe in the input (more ranks than work) is tolerated
     b2 = stripes.rebalance([(0, 0), (0, 544), (544, 1080)], [0.0, 1.0, 1.0], H)
     stripes.check_bounds(b2, H)
+
+
+def test_retries_are_local_and_every_frame_is_gathered_exactly_once():
+    """The multi-rank harness logic that went wrong in round 2: a rank whose frame is abandoned on the
+    device must repeat it with local work only.  A fake context abandons some frames (the NEXT call
+    reports it, like splat_render_device / splat_get_timings do); whatever happens, the loop issues
+    one gather per frame, every frame ends up rendered, and a non-retry error still propagates."""
+    from splat_b200 import stripes
+
+    class Retry(Exception):
+        pass
+
+    class FakeCtx:
+        def __init__(self, abandon):
+            self.abandon, self.pending, self.done, self.calls = set(abandon), False, [], 0
+
+        def render(self, i):
+            self.calls += 1
+            if self.pending:                 # the previous frame was abandoned: reported once, nothing enqueued
+                self.pending = False
+                raise Retry()
+            if i in self.abandon:
+                self.abandon.discard(i)      # it will fit next time (buffers grown)
+                self.pending = True
+                return
+            self.done.append(i)
+
+        def timings(self):
+            if self.pending:
+                self.pending = False
+                raise Retry()
+            return {"total_ms": 1.0}
+
+    is_retry = lambda e: isinstance(e, Retry)
+    for abandon in ([], [3], [0, 1, 2], [5, 6, 9]):
+        ctx, gathers, repeated = FakeCtx(abandon), 0, 0
+        for i in range(10):
+            repeated += stripes.render_with_retry(ctx.render, i, is_retry)
+            gathers += 1                                     # exactly one collective per frame
+            if i % 2:
+                tm, rep = stripes.timings_with_retry(ctx.timings, ctx.render, i, is_retry)
+                repeated += rep
+                assert tm["total_ms"] == 1.0
+        stripes.timings_with_retry(ctx.timings, ctx.render, 9, is_retry)
+        assert gathers == 10
+        assert set(ctx.done) == set(range(10)), (abandon, ctx.done)       # every frame was rendered in the end
+        assert (repeated > 0) == bool(abandon)
+
+    def boom(i):
+        raise ValueError("not a retry")
+    with pytest.raises(ValueError):
+        stripes.render_with_retry(boom, 0, is_retry)
