@@ -267,6 +267,10 @@ int splat_debug_read_tiles(splat_ctx *ctx, int which, uint32_t *out, uint64_t ca
  * contributed to: rgba[4*(y*W+x)] = r, g, b, 1-T (NaN where the pixel was not touched). */
 int splat_debug_render_float(splat_ctx *ctx, const splat_camera *cam, uint32_t *fb_inout, uint32_t W, uint32_t H,
                              float *rgba);
+/* Host only (no device, no context): the stripe partition rules of a group context.  ms == NULL: the
+ * initial cut, equal numbers of tile rows.  Otherwise bounds[2*parts] holds the current [row0,row1) per
+ * member and ms[parts] the members' measured frame times; bounds is replaced by the re-cut partition. */
+int splat_debug_partition(uint32_t *bounds, const float *ms, int32_t parts, uint32_t H);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,7 @@ EXPORTS = ["splat_abi_version", "splat_config_default", "splat_create", "splat_c
            "splat_render_rows", "splat_render_device", "splat_get_timings", "splat_get_tile_loads", "splat_pin_host",
            "splat_unpin_host", "splat_debug_project", "splat_debug_read_order",
            "splat_debug_sort_pairs", "splat_debug_blend_stats", "splat_debug_render_float", "splat_debug_read_tiles",
+           "splat_debug_partition",
            "splat_create_multi", "splat_group_get_bounds", "splat_comm_unique_id", "splat_comm_init_rank",
            "splat_comm_broadcast_scene", "splat_gather_stripes"]
 
@@ -98,6 +99,7 @@ def load():
     L.splat_debug_blend_stats.argtypes = [vp, vp, C.c_int]
     L.splat_debug_render_float.argtypes = [vp, C.POINTER(SplatCamera), vp, C.c_uint32, C.c_uint32, vp]
     L.splat_debug_read_tiles.argtypes = [vp, C.c_int, vp, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.splat_debug_partition.argtypes = [vp, vp, C.c_int32, C.c_uint32]
     L.splat_create_multi.argtypes = [C.POINTER(vp), C.POINTER(SplatConfig), C.POINTER(C.c_int32), C.c_int32]
     L.splat_group_get_bounds.argtypes = [vp, vp, C.c_int32, C.POINTER(C.c_int32)]
     L.splat_comm_unique_id.argtypes = [vp]
@@ -108,6 +110,21 @@ def load():
         getattr(L, name)  # AttributeError if the .so does not export it
     _lib = L
     return L
+
+
+def group_partition(H: int, parts: int, bounds=None, times_ms=None):
+    """The library's own stripe partition rules, on the host (splat_debug_partition): the initial equal cut,
+    or -- given the current bounds and the members' measured frame times -- the re-cut one."""
+    L = load()
+    flat = (C.c_uint32 * (2 * parts))()
+    ms = None
+    if times_ms is not None:
+        flat[:] = [int(v) for b in bounds for v in b]
+        ms = (C.c_float * parts)(*[float(t) for t in times_ms])
+    rc = L.splat_debug_partition(flat, ms, parts, H)
+    if rc:
+        raise SplatError(rc, "splat_debug_partition")
+    return [(int(flat[2 * k]), int(flat[2 * k + 1])) for k in range(parts)]
 
 
 def camera_struct(camera) -> SplatCamera:

@@ -469,7 +469,7 @@ blend_kernel(const uint2 *__restrict__ ranges, const uint2 *__restrict__ units,
     mbar_init(&S.stage_bar, 1);
   }
   __syncthreads();
-  uint32_t stage_par = 0;   // phase parity of stage_bar: one phase per staged batch, all attempts
+  [[maybe_unused]] uint32_t stage_par = 0;   // phase parity of stage_bar: one phase per staged batch, all attempts
   if (w >= BL_PRODUCER_THREADS / 32 + ng) return;   // split units: the spare consumer warps have nothing to do
   const uint32_t nsync = BL_PRODUCER_THREADS + 32u * ng;   // threads that take part in this unit
   const f32x2 NZ = P.nz2;

@@ -1512,6 +1512,19 @@ int splat_debug_sort_pairs(splat_ctx *c, uint32_t *keys, uint32_t *vals, uint64_
   return rc;
 }
 
+int splat_debug_partition(uint32_t *bounds, const float *ms, int32_t parts, uint32_t H) {
+  if (!bounds || parts < 1 || H == 0) return SPLAT_ERR_INVALID;
+  std::vector<uint32_t> b;
+  if (!ms) {
+    equal_bounds(b, H, parts);
+  } else {
+    b.assign(bounds, bounds + (size_t)2 * parts);
+    rebalance_bounds(b, std::vector<float>(ms, ms + parts), H);
+  }
+  std::copy(b.begin(), b.end(), bounds);
+  return SPLAT_OK;
+}
+
 int splat_debug_read_tiles(splat_ctx *c, int which, uint32_t *out, uint64_t cap_words, uint64_t *n_words) {
   // tests / diagnostics: per-tile arrays of the last frame.  which: 0 = list ranges (2 words per tile),
   // 1 = far_cnt (cut Gaussians per tile), 2 = tile_failed

@@ -215,3 +215,38 @@ def test_retries_are_local_and_every_frame_is_gathered_exactly_once():
         raise ValueError("not a retry")
     with pytest.raises(ValueError):
         stripes.render_with_retry(boom, 0, is_retry)
+
+
+def test_library_partition_rules_agree_with_the_python_ones():
+    """splat_api.cu's equal_bounds / rebalance_bounds (what a group context uses) through the host-only
+    export splat_debug_partition, against stripes.stripe_bounds / stripes.rebalance: the same cover rules
+    and, for the re-cut, the same bottleneck (the cuts themselves may differ where several are optimal)."""
+    from splat_b200 import _lib
+
+    rng = np.random.default_rng(7)
+    for H in (16, 17, 150, 720, 1080, 2160):
+        for parts in (1, 2, 3, 4, 8):
+            eq = _lib.group_partition(H, parts)
+            stripes.check_bounds(eq, H)
+            assert eq == stripes.stripe_bounds(H, parts)
+            for _ in range(6):
+                times = rng.uniform(0.2, 3.0, parts)
+                times[[k for k, (a, b) in enumerate(eq) if b == a]] = 0.0      # an empty stripe takes no time
+                lib_b = _lib.group_partition(H, parts, eq, times)
+                py_b = stripes.rebalance(eq, times, H)
+                stripes.check_bounds(lib_b, H)
+
+                # predicted time of the heaviest stripe under the model both sides use (uniform cost per tile row)
+                tr = stripes.tile_rows(H)
+                w = np.zeros(tr)
+                for (a, b), t in zip(eq, times):
+                    t0, t1 = a // 16, (b + 15) // 16
+                    if t1 > t0:
+                        w[t0:t1] = max(float(np.float32(t)), 1e-4) / (t1 - t0)
+
+                def worst(bounds):
+                    return max(w[a // 16:(b + 15) // 16].sum() for a, b in bounds)
+
+                assert worst(lib_b) <= worst(py_b) * (1 + 1e-5) + 1e-9, (H, parts, times, lib_b, py_b)
+                assert worst(py_b) <= worst(lib_b) * (1 + 1e-5) + 1e-9, (H, parts, times, lib_b, py_b)
+                assert worst(lib_b) <= worst(eq) * (1 + 1e-6)                  # never worse than what it started from
