@@ -108,3 +108,17 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b|liboracle|splat_oracle", txt, flags=re.M):
                     bad.append(f)
     assert not bad, bad
+
+
+def test_docs_only_name_entry_points_the_header_declares():
+    """INTEGRATION.md (the binding a maintainer would add), README.md and DESIGN.md must not drift from include/splat.h"""
+    import re
+
+    hdr = open(os.path.join(ROOT, "include", "splat.h")).read()
+    declared = set(re.findall(r"\bsplat_[a-z0-9_]+\b", hdr))
+    not_symbols = {"splat_", "splat_comm_", "splat_demo", "splat_expf", "splat_oracle", "splat_pipeline", "splat_sys", "splat_b200",
+                   "splat_api", "splat_upload_"}
+    for doc in ("INTEGRATION.md", "README.md", "DESIGN.md"):
+        names = set(re.findall(r"\bsplat_[a-z0-9_]*", open(os.path.join(ROOT, doc)).read()))
+        unknown = sorted(n for n in names - declared - not_symbols if not n.endswith("_"))
+        assert not unknown, f"{doc} names {unknown}, which include/splat.h does not declare"
