@@ -10,6 +10,7 @@
 //   splat_demo render  FILE|naive H W x y z FRAMES YAW_STEP PIPELINE(1|2) CLEARED(0|1) OUT
 //                                                     FRAMES frames, the camera yawed by YAW_STEP before each;
 //                                                     per frame: splat_camera bytes then W*H u32 pixels -> OUT
+//                                                     env SPLAT_DEMO_DEVICES=0,1,..: a group context over those GPUs
 // Exit codes: 0 ok, 2 usage, 3 a splat_b200::Error (message on stderr).  There is no CPU path: `render`
 // on a box without a usable GPU exits 3 with the library's message.
 #include <cstdio>
@@ -98,11 +99,19 @@ int main(int argc, char **argv) {
           put(f, color.raw(), (size_t)W * (size_t)H * 4);
         }
       };
+      std::vector<int32_t> devices;
+      if (const char *d = std::getenv("SPLAT_DEMO_DEVICES")) {
+        for (const char *q = d; *q;) {
+          devices.push_back((int32_t)std::strtol(q, const_cast<char **>(&q), 10));
+          if (*q == ',') ++q;
+        }
+      }
+      if (devices.empty()) devices.push_back(0);
       if (which == 1) {
-        GaussianSplatPipeline01 p(std::move(gs), camera);
+        GaussianSplatPipeline01 p(std::move(gs), camera, devices);
         loop(p);
       } else {
-        GaussianSplatPipeline02 p(GaussianList::from_vec(gs), camera);
+        GaussianSplatPipeline02 p(GaussianList::from_vec(gs), camera, devices);
         loop(p);
         const splat_timings t = p.timings();
         std::fprintf(stderr, "splat_demo: %llu Gaussians, %llu visible, %llu tile instances, last frame %.3f ms\n",

@@ -400,12 +400,17 @@ inline std::vector<Gaussian> load_from_ply(const std::string &filename) {
 // OUT of the pipeline structs' public fields, like the shim of INTEGRATION.md keeps its handle.
 class Device {
  public:
-  explicit Device(float lowpass, int device = 0) {
+  explicit Device(float lowpass, int device = 0) : Device(lowpass, std::vector<int32_t>{device}) {}
+  // several devices: a group context -- the frame is sharded by screen-tile stripes, the scene broadcast at
+  // upload, the stripes gathered over NVLink inside splat_render (splat.h, "Multi-GPU"); same pixels
+  Device(float lowpass, const std::vector<int32_t> &devices) {
+    if (devices.empty()) throw Error(SPLAT_ERR_INVALID, "no device listed");
     splat_config cfg;
     splat_config_default(&cfg);
-    cfg.device = device;
+    cfg.device = devices[0];
     cfg.lowpass = lowpass;
-    const int rc = splat_create(&ctx_, &cfg);
+    const int rc = devices.size() == 1 ? splat_create(&ctx_, &cfg)
+                                       : splat_create_multi(&ctx_, &cfg, devices.data(), (int32_t)devices.size());
     if (rc != SPLAT_OK) throw Error(rc, std::string("splat_create: ") + splat_create_error());   // no CPU fallback
   }
   Device(const Device &) = delete;
@@ -440,6 +445,8 @@ class GaussianSplatPipeline01 {
   Camera camera;
   GaussianSplatPipeline01(std::vector<Gaussian> g, Camera c, int device = 0)
       : gaussians(std::move(g)), camera(std::move(c)), dev_(0.01f, device) {}
+  GaussianSplatPipeline01(std::vector<Gaussian> g, Camera c, const std::vector<int32_t> &devices)
+      : gaussians(std::move(g)), camera(std::move(c)), dev_(0.01f, devices) {}
   // pipelines.rs:66-86.  `color` is blended onto and overwritten.
   void render_to_buffer(Buffer2d<uint32_t> &color) {
     if (!dev_.holds(gaussians.data(), gaussians.size())) {
@@ -463,6 +470,8 @@ class GaussianSplatPipeline02 {
   GaussianList gaussians;
   Camera camera;
   GaussianSplatPipeline02(GaussianList g, Camera c, int device = 0) : gaussians(std::move(g)), camera(std::move(c)), dev_(0.3f, device) {}
+  GaussianSplatPipeline02(GaussianList g, Camera c, const std::vector<int32_t> &devices)
+      : gaussians(std::move(g)), camera(std::move(c)), dev_(0.3f, devices) {}
   // pipelines.rs:260-280
   void render_to_buffer(Buffer2d<uint32_t> &color) {
     upload_if_needed();

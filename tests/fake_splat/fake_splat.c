@@ -37,6 +37,13 @@ int splat_create(splat_ctx **out, const splat_config *cfg) {
   *out = c;
   return SPLAT_OK;
 }
+int splat_create_multi(splat_ctx **out, const splat_config *cfg, const int32_t *devices, int32_t n) {
+  int rc = splat_create(out, cfg);
+  if (rc) return rc;
+  const char *log = getenv("FAKE_SPLAT_LOG");
+  if (log) { FILE *f = fopen(log, "a"); if (f) { fprintf(f, "group of %d:", n); for (int i = 0; i < n; ++i) fprintf(f, " %d", devices[i]); fprintf(f, "\n"); fclose(f); } }
+  return SPLAT_OK;
+}
 const char *splat_create_error(void) { return g_create_error; }
 void splat_destroy(splat_ctx *c) {
   if (!c) return;
