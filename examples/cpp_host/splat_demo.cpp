@@ -6,6 +6,7 @@
 //   splat_demo camera  H W x y z yaw pitch OUT        splat_camera struct bytes of that pose -> OUT
 //   splat_demo ply     FILE OUT                       load_from_ply -> from_vec: N (u64) then positions |
 //                                                     scales | opacities | rotations | sh -> OUT
+//   splat_demo trim    SRC DST COUNT                  the first COUNT vertices of a PLY (00_ply_load.rs:9-63)
 //   splat_demo naive   OUT                            the 4-Gaussian scene, same dump
 //   splat_demo render  FILE|naive H W x y z FRAMES YAW_STEP PIPELINE(1|2) CLEARED(0|1) OUT
 //                                                     FRAMES frames, the camera yawed by YAW_STEP before each;
@@ -39,7 +40,7 @@ static void dump_list(const GaussianList &l, const char *path) {
 }
 
 static int usage() {
-  std::fprintf(stderr, "usage: splat_demo camera|ply|naive|render ...  (see the header of splat_demo.cpp)\n");
+  std::fprintf(stderr, "usage: splat_demo camera|ply|trim|naive|render ...  (see the header of splat_demo.cpp)\n");
   return 2;
 }
 
@@ -62,6 +63,10 @@ int main(int argc, char **argv) {
     }
     if (mode == "ply" && argc == 4) {
       dump_list(GaussianList::from_vec(load_from_ply(argv[2])), argv[3]);
+      return 0;
+    }
+    if (mode == "trim" && argc == 5) {
+      std::printf("%zu\n", trim_ply(argv[2], argv[3], (size_t)std::atoll(argv[4])));
       return 0;
     }
     if (mode == "naive" && argc == 3) {

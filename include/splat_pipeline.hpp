@@ -20,6 +20,7 @@
 #ifndef SPLAT_B200_PIPELINE_HPP
 #define SPLAT_B200_PIPELINE_HPP
 
+#include <algorithm>
 #include <array>
 #include <cmath>
 #include <cstdint>
@@ -393,6 +394,45 @@ inline std::vector<Gaussian> load_from_ply(const std::string &filename) {
       for (int k = 0; k < 3; ++k) g.position[k] -= avg[k];
   }
   return out;
+}
+
+// `trim` (src/bin/00_ply_load.rs:9-63): copy the first `count` vertices of a binary_little_endian PLY into a
+// new file whose header differs only in the vertex count (tiny test scenes).  Returns the vertices written.
+inline size_t trim_ply(const std::string &src, const std::string &dst, size_t count = 3) {
+  std::ifstream f(src, std::ios::binary);
+  if (!f) throw Error(0, "cannot open " + src);
+  std::string data((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  const std::string marker = "end_header\n";
+  const size_t hpos = data.find(marker);
+  if (data.compare(0, 3, "ply") != 0 || hpos == std::string::npos) throw Error(0, src + ": not a PLY file");
+  const size_t body = hpos + marker.size();
+  std::string out_header, line;
+  std::istringstream header(data.substr(0, body));
+  size_t n = 0, stride = 0;
+  while (std::getline(header, line)) {
+    std::istringstream ls(line);
+    std::string tok, a, b;
+    ls >> tok >> a >> b;
+    if (tok == "element") {
+      if (a != "vertex") throw Error(0, "Unexpected element!");
+      n = (size_t)std::strtoull(b.c_str(), nullptr, 10);
+      line = "element vertex " + std::to_string(std::min(n, count));
+    } else if (tok == "property") {
+      detail::PlyProp p;
+      if (!detail::ply_type(a, &p)) throw Error(0, src + ": unsupported property type " + a);
+      stride += (size_t)p.size;
+    } else if (tok == "format" && a != "binary_little_endian") {
+      throw Error(0, "trim_ply handles binary_little_endian files");
+    }
+    out_header += line + "\n";
+  }
+  const size_t m = std::min(n, count);
+  if (data.size() < body + m * stride) throw Error(0, src + ": truncated vertex payload");
+  std::ofstream o(dst, std::ios::binary);
+  if (!o) throw Error(0, "cannot write " + dst);
+  o.write(out_header.data(), (std::streamsize)out_header.size());
+  o.write(data.data() + body, (std::streamsize)(m * stride));
+  return m;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -133,6 +133,19 @@ def test_ply_with_another_element_is_the_reference_panic(demo, tmp_path):
     assert p.returncode == 3 and "cannot open" in p.stderr
 
 
+def test_trim_writes_the_same_file_as_the_python_mirror(demo, tmp_path):
+    from splat_b200.gaussians import trim_ply
+
+    src, a, b = tmp_path / "s.ply", tmp_path / "a.ply", tmp_path / "b.ply"
+    save_ply(str(src), raw_scene(40))
+    for count in (3, 40, 100):
+        p = run(demo, "trim", src, a, count)
+        assert int(p.stdout) == trim_ply(str(src), str(b), count) == min(count, 40)
+        assert load_ply_soa(str(a)).num_gaussians == min(count, 40)
+        assert a.read_bytes().split(b"end_header\n", 1)[1] == b.read_bytes().split(b"end_header\n", 1)[1]
+        assert a.read_bytes().split(b"end_header\n", 1)[0].split() == b.read_bytes().split(b"end_header\n", 1)[0].split()
+
+
 @pytest.fixture(scope="module")
 def fake_lib_dir(tmp_path_factory, orc):
     d = tmp_path_factory.mktemp("fake_splat")
