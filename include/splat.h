@@ -81,11 +81,13 @@ typedef struct {
   int32_t  blend_mode;     /* SPLAT_BLEND_*: 0 = the reference's quantised far->near blend (parity) */
   int32_t  near_cut;       /* The reference blend reads only the nearest few hundred entries of a tile list (exact
                             * early termination), so a frame first bins + sorts only the nearest k/1024 of the
-                            * Gaussians and redoes the tiles that do not converge on them with all of them.
-                            * Pixels are identical either way.  -1 (default) = automatic: starts at 1/8 once a
-                            * scene shows >= 200k visible Gaussians, doubles after a whole-frame fall-back;
-                            * 0 = off; 1..1024 = fixed fraction.  Near-cut frames read two status words on the
-                            * host per frame; frames without it need no host wait at all.                      */
+                            * Gaussians; tiles that only a few of the cut Gaussians touch get those binned after all
+                            * ("open" tiles), and a frame whose near lists still do not suffice is abandoned on the
+                            * device and repeated without the cut (host-buffer calls do that themselves;
+                            * splat_render_device reports SPLAT_ERR_RETRY).  Pixels are identical either way.
+                            * -1 (default) = automatic: 1/8 once a scene shows >= 200k visible Gaussians and tile
+                            * lists of >= 2048 entries on average, doubled after any failure; 0 = off;
+                            * 1..1024 = fixed fraction.  Nothing is read on the host during a frame.           */
   int32_t  sync_frames;    /* 1: read the tile-instance count on the host in the middle of every frame (exact
                             * launch sizes, one round trip per frame).  0 (default): only the first frame of a
                             * target geometry does; later frames are enqueued without any host wait            */
@@ -123,12 +125,14 @@ typedef struct {
   uint64_t near_cut_rank;   /* depth ranks below this were left out of the first binning pass (0 = none) */
   uint64_t near_cut_failed; /* pixel groups / tiles that did not converge in that pass (0 = it was enough) */
   uint64_t near_cut_instances; /* (tile, Gaussian) pairs that pass did not have to bin and sort */
-  uint64_t frames_skipped;  /* since the context was created: frames whose tile instances did not fit the buffers
-                             * on the no-round-trip path (host-buffer calls repeat them themselves)            */
-  uint64_t second_pass_instances; /* near-cut frames: (tile, Gaussian) pairs the second pass binned for the tiles that
-                                   * did not converge on the near lists (0 = it had nothing to do)            */
-  uint64_t near_cut_fallbacks;    /* since the context was created: near-cut frames whose second pass had work */
-  float    second_pass_ms;  /* that second pass (included in total_ms)                      */
+  uint64_t frames_skipped;  /* since the context was created: frames abandoned on the device on the no-round-trip
+                             * path -- their tile instances outgrew the launch bounds, or their near lists did
+                             * not suffice (host-buffer calls repeat them themselves)                          */
+  uint64_t second_pass_instances; /* `make cdp` build only (a second pass launched from the device instead of a
+                                   * repeated frame): pairs that pass binned for the tiles that did not converge
+                                   * on the near lists; 0 in the shipped build                                  */
+  uint64_t near_cut_fallbacks;    /* since the context was created: near-cut frames whose near lists did not suffice */
+  float    second_pass_ms;  /* the device-side check of the near pass (and, `make cdp`, the second pass); in total_ms */
   float    reserved_;
 } splat_timings;
 

@@ -1,11 +1,15 @@
 // splat_api.cu -- the C ABI of include/splat.h: context, scene upload, frame orchestration.
 //
 // Frame = render_to_buffer (pipelines.rs:66-86 / :260-280):
-//   K1 project -> K3a depth radix sort (N keys) -> K2 tile count + scan -> [host reads the
-//   instance count] -> K2 emit -> K3b tile radix sort (I keys) -> K4 ranges -> K5 blend.
-// One host<->device round trip per frame (the instance count), everything else is enqueued
-// asynchronously on one stream; the framebuffer upload runs on a second stream and is only
-// waited for by the blend kernel.
+//   K1 project -> K3a depth radix sort (N keys) -> [near cut: K4b far_cover / far_prefix] -> K2 tile
+//   count + scan -> K2 emit -> K3b tile radix sort (I keys) -> K4 ranges + unit order -> K5 blend
+//   -> [near cut: one kernel that checks on the device whether the near lists sufficed].
+// Only the first frame of a target geometry (and the repeat of an abandoned frame) reads the
+// tile-instance count on the host; every other frame is enqueued without any host wait: launches are
+// sized from the previous frame, the kernels read the real counts from device memory, and a frame
+// that outgrows its bounds is abandoned on the device and repeated (render_frame, finish_frame).
+// Everything runs on one stream; the framebuffer upload runs on a second stream and is only waited
+// for by the blend kernel.  Multi-GPU (group contexts, per-rank communicators) is at the end.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -311,8 +315,11 @@ __global__ void __launch_bounds__(256) fill_u32_kernel(uint32_t *p, uint32_t v, 
     if (i0 + k < n) p[i0 + k] = v;
 }
 
-// ---------------------------------------------------------------- near cut: the second pass, launched ON THE DEVICE
+// ---------------------------------------------------------------- near cut: the check after the near pass, on the device
 // After the first (near) pass of a near-cut frame the device knows which tiles did not converge.
+// Shipped build (SPLAT_CDP = 0): pass_b_setup_kernel only records that (FrameStatus::overflow /
+// skipped) and the frame is repeated without the cut.  `make cdp` (SPLAT_CDP = 1, -rdc=true, measured
+// 4-6% slower overall: profiles/r2p_ab_cdp_rdc.txt) instead runs a second pass from the device:
 // pass_b_setup_kernel (bin.cuh) is the only thing the host enqueues for the second pass; if there
 // is work it starts this chain with CUDA dynamic parallelism -- tail launches, which run in order
 // after the launching grid and before the next kernel of the host's stream -- and every launch is
