@@ -96,6 +96,7 @@ def install(setattr_, orc, abandon_at=(3,), make_scene=None):
 
         def render_device(self, cs, ptr, W, H, r0=0, r1=None, stream=0):
             r1 = H if r1 is None else r1
+            self.last_rows = r1 - r0
             self._maybe_retry()
             log.renders += 1
             if log.renders in abandon_at:
@@ -124,8 +125,7 @@ def install(setattr_, orc, abandon_at=(3,), make_scene=None):
             stripes.gather_stripes(t, [tuple(b) for b in bounds], self.rank, root)
 
         def tile_loads(self, tiles_x):
-            tr = (self.last_h + 15) // 16 if hasattr(self, "last_h") else 6
-            return np.ones((tr, tiles_x), np.uint32)
+            return np.ones(((self.last_rows + 15) // 16, tiles_x), np.uint32)      # of the last rendered stripe
 
         def timings(self):
             self._maybe_retry()
