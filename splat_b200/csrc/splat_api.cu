@@ -796,11 +796,12 @@ int finish_frame(splat_ctx *c) {
   }
   for (int tries = 0; c->retry_pending && tries < 3; ++tries) {
     c->retry_pending = false;
-    c->retried += 1;
     int rc = ensure_instances(c, grow_target(c));
     if (rc) return rc;
+    const uint32_t retried = c->retried;
     rc = render_frame(c, c->last_params, c->last_fb, c->last_stream, nullptr, true);
     if (rc) return rc;
+    c->retried += retried + 1;         // render_frame starts its count at 0: this frame is a repeat
     rc = wait_done(c, last_status_event(c), c->last_stream, "frame (repeat)");
     if (rc) return rc;
     absorb_status(c);

@@ -31,15 +31,49 @@ def _rows(ptr, rows, W):
     return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint32)), shape=(rows, W))
 
 
-def install(setattr_, orc, abandon_at=(3,), make_scene=None):
-    """setattr_(obj, name, value) applies one patch (pytest's monkeypatch.setattr, or plain setattr in a spawned
-    worker).  `abandon_at`: ordinal numbers of render_device calls after which the NEXT call (render or
-    timings) reports SPLAT_ERR_RETRY once, the way the library reports a frame abandoned on the device."""
+def install_emulated(setattr_, emu_path, make_scene=None):
+    """Like install(), but the library is the REAL one -- splat_api.cu and the kernels compiled for the host
+    (tests/cuda_emu) -- so frames, counts, timings and retry semantics are the product's own.  Only what needs NCCL is
+    replaced: the scene broadcast (every rank generates the same seeded scene) and the stripe gather (gloo)."""
     import torch
     import torch.distributed as dist
 
     from splat_b200 import _lib, stripes
 
+    _patch_torch(setattr_, torch, dist)
+    setattr_(_lib, "LIB_PATH", emu_path)
+    setattr_(_lib, "_lib", None)
+    _lib.load()
+    log = types.SimpleNamespace(gathers=0, contexts=[])
+    Real = _lib.Context
+
+    class EmuContext(Real):
+        def __init__(self, device=0, **kw):
+            super().__init__(device=0, **kw)              # the emulated box has one device
+            self.kw, self.rank = dict(kw), 0
+            log.contexts.append(self)
+
+        def unique_id(self):
+            return bytes(128)
+
+        def comm_init(self, uid, n_ranks, rank):
+            self.rank = rank
+
+        def broadcast_scene(self, root, n):
+            if self.rank != root:
+                self.upload(make_scene(n))
+            self.n = n
+
+        def gather_stripes(self, ptr, W, H, bounds, root=0, stream=0):
+            log.gathers += 1
+            t = torch.from_numpy(_rows(ptr, H, W).view(np.int32))
+            stripes.gather_stripes(t, [tuple(b) for b in bounds], self.rank, root)
+
+    setattr_(_lib, "Context", EmuContext)
+    return log
+
+
+def _patch_torch(setattr_, torch, dist):
     real_device = torch.device
     real_init = dist.init_process_group
     setattr_(torch, "device", lambda *a, **k: real_device("cpu"))
@@ -51,6 +85,17 @@ def install(setattr_, orc, abandon_at=(3,), make_scene=None):
     setattr_(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
     setattr_(dist, "init_process_group", lambda backend=None, **k: real_init("gloo"))
 
+
+def install(setattr_, orc, abandon_at=(3,), make_scene=None):
+    """setattr_(obj, name, value) applies one patch (pytest's monkeypatch.setattr, or plain setattr in a spawned
+    worker).  `abandon_at`: ordinal numbers of render_device calls after which the NEXT call (render or
+    timings) reports SPLAT_ERR_RETRY once, the way the library reports a frame abandoned on the device."""
+    import torch
+    import torch.distributed as dist
+
+    from splat_b200 import _lib, stripes
+
+    _patch_torch(setattr_, torch, dist)
     log = types.SimpleNamespace(gathers=0, renders=0, retries_reported=0, contexts=[])
 
     class FakeContext:

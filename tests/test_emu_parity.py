@@ -103,3 +103,120 @@ def test_stripe_frames_with_a_host_round_trip_in_every_frame(lib, orc):
     assert max(kept) > 0.3 and min(kept) < 0.3                        # both projection paths were taken
     for c in ctxs:
         c.close()
+
+
+@pytest.mark.parametrize("which,cleared,n,W,H", [(2, 0, 3000, 320, 240), (2, 1, 3000, 320, 240), (1, 0, 1500, 200, 150)])
+def test_cpp_viewer_loop_on_the_emulated_library(lib, cpp_demo, tmp_path, orc, which, cleared, n, W, H):
+    """tests/test_zz_cpp_host_gpu.py without the GPU: examples/cpp_host/splat_demo (the C++ mirror of the reference's
+    interface) bound at load time to the emulated build of the real library instead of the CUDA one"""
+    import numpy as np
+
+    from test_cpp_host import oracle_frame, raw_scene, read_frames, read_list, run
+
+    from splat_b200.gaussians import save_ply
+
+    libdir = tmp_path / "lib"
+    libdir.mkdir()
+    os.symlink(lib.LIB_PATH, libdir / "libsplat_b200.so")
+    env = {"LD_LIBRARY_PATH": str(libdir)}
+    frames, step = 3, 0.35
+    ply, scene_dump, out = tmp_path / "s.ply", tmp_path / "s.bin", tmp_path / "frames.bin"
+    save_ply(str(ply), raw_scene(n))
+    run(cpp_demo, "ply", ply, scene_dump)
+    scene = read_list(scene_dump)
+    run(cpp_demo, "render", ply, H, W, 0.0, 0.0, 3.0, frames, step, which, cleared, out, env=env)
+    got = read_frames(out, W, H)
+    assert len(got) == frames
+    for k, (cs, fb) in enumerate(got):
+        ref = oracle_frame(orc, scene, cs, W, H, 0.01 if which == 1 else 0.3)
+        assert np.count_nonzero(ref) > 1000
+        assert np.array_equal(fb, ref), f"frame {k}: {np.count_nonzero(fb != ref)} of {W * H} pixels differ"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# bench.py on the real library (emulated): the harness with the product's own frame, count, timing and retry
+# semantics -- tests/test_bench_flow.py runs the same flows on a stand-in that renders with the oracle
+def test_bench_single_rank_on_the_emulated_library(lib, monkeypatch, orc, capfd):
+    import importlib
+    import json
+
+    import _fake_gpu
+
+    bench = importlib.import_module("bench")
+    _fake_gpu.install_emulated(monkeypatch.setattr, lib.LIB_PATH, make_scene=bench.make_scene)
+    _fake_gpu.quiet_bench(monkeypatch.setattr, bench)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--gaussians", "1500", "--width", "160", "--height", "96", "--steps", "2", "--warmup", "3"])
+    for k in ("WORLD_SIZE", "RANK", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    assert bench.main() == 0
+    out = capfd.readouterr().out.strip().splitlines()
+    assert len(out) == 1
+    line = json.loads(out[0])
+    assert line["parity"]["mismatching_pixels"] == 0 and line["parity"]["rows"] == 96 and line["parity"]["covered_pixels"] > 1000
+    assert line["gpu_launches"] >= 2 * 20 and line["instances_per_frame"] > 0
+    assert line["stages_ms"]["blend_ms"] > 0 and line["e2e"]["value"] > 0 and line["e2e_cleared"]["value"] > 0
+    assert line["frames_repeated"] == 0
+
+
+def _emu_rank_main(rank, world, port, mode, emu_path, q):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world),
+                      EMU_WORKERS="3")
+    import _fake_gpu
+    import bench
+
+    log = _fake_gpu.install_emulated(setattr, emu_path, make_scene=bench.make_scene)
+    lines = []
+    _fake_gpu.quiet_bench(setattr, bench, sink=lines.append)
+    sys.argv = ["bench.py", "--gpus", str(world), "--gaussians", "3000", "--width", "160", "--height", "128", "--steps", "2", "--warmup", "3",
+                "--stripe-mode", mode]
+    rc = bench.main()
+    ctx = log.contexts[0]
+    q.put({"rank": rank, "rc": rc, "lines": lines, "gathers": log.gathers, "sync_frames": ctx.kw.get("sync_frames")})
+
+
+@pytest.mark.parametrize("mode", ["sync", "async"])
+def test_bench_two_ranks_on_the_emulated_library(lib, orc, mode):
+    """two processes, each with the real library (emulated) rendering its stripe, stripes gathered over gloo: the
+    frame that reaches rank 0's host buffer is the oracle's whole frame"""
+    import torch.multiprocessing as mp
+
+    from test_bench_flow import _check_line, _expected_checksum, _free_port
+
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    port = _free_port()
+    procs = [mpc.Process(target=_emu_rank_main, args=(r, 2, port, mode, lib.LIB_PATH, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=900) for _ in procs), key=lambda r: r["rank"])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    r0, r1 = res
+    assert r0["rc"] == 0 and r1["rc"] == 0 and len(r0["lines"]) == 1 and r1["lines"] == []
+    line = r0["lines"][0]
+    _check_line(line, 2, 2, 3)
+    assert r0["gathers"] == r1["gathers"] > 0
+    assert r0["sync_frames"] == (1 if mode == "sync" else 0)
+    assert line["frame_checksum"] == _expected_checksum(orc, n=3000, W=160, H=128)
+
+
+def test_a_repeated_frame_is_counted_as_retried(lib):
+    """found with the emulator: finish_frame's increment of frames_retried was wiped by the repeat's own reset"""
+    import numpy as np
+
+    from test_gpu_parity import _camera, _scene
+
+    W, H = 320, 200
+    scene = _scene(40_000, 0x5EED0072, -3.4)
+    ctx = lib.Context(device=0, max_instances=1)
+    ctx.upload(scene)
+    for pos in ((0.0, 0.0, 40.0), (0.0, 0.0, 40.0), (0.0, 0.0, 1.5)):
+        fb = np.zeros((H, W), np.uint32)
+        ctx.render(lib.camera_struct(_camera(W, H, pos)), fb)
+    t = ctx.timings()
+    assert t["frames_skipped"] == 1 and t["frames_retried"] == 1
+    ctx.close()
