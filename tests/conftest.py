@@ -12,6 +12,29 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+# tests/test_emu_parity.py: the emulated runs that take more than a few seconds each only run on request, so that the
+# default CPU suite stays within a couple of minutes (SPLAT_EMU_FULL=1 runs all of them: about five minutes)
+EMU_ON_REQUEST = (
+    "test_frames_without_a_host_round_trip", "test_near_cut_stripes_and_empty_regions", "test_near_cut_is_exact[128-None]",
+    "test_near_cut_is_exact[512-False]", "test_a_repeated_frame_is_counted_as_retried", "test_framebuffer_bit_exact[inside_cloud]",
+    "test_framebuffer_bit_exact[demo_cam_100k]", "test_float_blend_matches_float_oracle[demo_cam_100k_720p]",
+    "test_render_device_stripes_into_one_device_frame", "test_stripes_equal_full_frame",
+    "test_deep_lists_exact_early_termination[deep_150k_128x96]", "test_deep_lists_exact_early_termination[deep_mixed_opacity]",
+    "test_deep_lists_exact_early_termination[deep_onto_noise]", "test_bench_two_ranks_on_the_emulated_library[async]",
+    "test_group_context_equals_single_device_and_oracle_emulated[equal_stripes]",
+    "test_cpp_viewer_loop_on_the_emulated_library[2-1-3000-320-240]", "test_cpp_viewer_loop_on_the_emulated_library[1-0-1500-200-150]",
+)
+
+
+def pytest_collection_modifyitems(config, items):
+    if os.environ.get("SPLAT_EMU_FULL") == "1":
+        return
+    skip = pytest.mark.skip(reason="emulated run on request only: SPLAT_EMU_FULL=1")
+    for item in items:
+        if item.nodeid.startswith("tests/test_emu_parity.py::") and item.name in EMU_ON_REQUEST:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def orc():
     """The CPU oracle (oracle/liboracle.so), built on demand with gcc."""

@@ -558,7 +558,7 @@ enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocMappe
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : (e == cudaErrorMemoryAllocation ? "out of memory" : "emulated CUDA error"); }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
-inline cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidValue; }
+inline cudaError_t cudaSetDevice(int d) { return d >= 0 && d < 64 ? cudaSuccess : cudaErrorInvalidValue; }   // "devices" are just ordinals
 inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 template <class T> cudaError_t cudaMalloc(T **p, size_t bytes) {
   void *q = nullptr;

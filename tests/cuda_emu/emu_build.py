@@ -18,6 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "splat_b200", "csrc")
 BUILD = os.path.join(HERE, "_build")
 OUT = os.path.join(BUILD, "libsplat_b200_emu.so")
+NCCL = os.path.join(BUILD, "libnccl_emu.so")     # in-process stand-in for libnccl (fake_nccl.cpp); the emulated build dlopens THIS
 
 
 # ------------------------------------------------------------------------------------------------ small C++ scanners
@@ -172,13 +173,16 @@ def preprocess(name):
     src = rewrite_extern_shared(src)
     src = rewrite_launches(src)
     src = src.replace('#include "../../include/splat.h"', f'#include "{os.path.join(ROOT, "include", "splat.h")}"')
+    if name == "comm.cuh":
+        assert src.count('"libnccl.so.2", "libnccl.so"') == 1
+        src = src.replace('"libnccl.so.2", "libnccl.so"', f'"{NCCL}"')
     assert "<<<" not in src and not re.search(r"\basm\b", src), name
     return src
 
 
 def build(force=False):
     srcs = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh") or f == "splat_api.cu")
-    deps = [os.path.join(CSRC, f) for f in srcs] + [os.path.join(HERE, f) for f in ("cuda_emu.h", "emu_build.py", "nccl.h", "cuda_runtime.h")]
+    deps = [os.path.join(CSRC, f) for f in srcs] + [os.path.join(HERE, f) for f in ("cuda_emu.h", "emu_build.py", "nccl.h", "cuda_runtime.h", "fake_nccl.cpp")]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT
     gen = os.path.join(BUILD, "src")
@@ -189,6 +193,8 @@ def build(force=False):
     cmd = [os.environ.get("CXX", "g++"), "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-frounding-math",
            "-fno-strict-aliasing", "-w", "-I", HERE, "-I", gen, "-o", OUT, os.path.join(gen, "splat_api.cpp"), "-ldl"]
     subprocess.check_call(cmd)
+    subprocess.check_call([os.environ.get("CXX", "g++"), "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-I", HERE,
+                           "-o", NCCL, os.path.join(HERE, "fake_nccl.cpp")])
     return OUT
 
 

@@ -3,7 +3,8 @@ tests/cuda_emu (threads of a block = fibers, inline PTX mapped to functions of t
 synchronous host calls) and driven through the same C ABI, by the SAME test functions as the GPU parity suite.
 What this checks without a GPU: the kernels' logic and the frame orchestration (sorts, binning, near cut and
 open tiles, abandoned frames, stripes, the blend's producer/consumer rings and exact early termination) give
-bit-identical pixels to the oracle.  What it cannot check: speed, and hardware-level races.  The emulated
+bit-identical pixels to the oracle.  What it cannot check: speed, and hardware-level races.  The runs that take
+more than a few seconds each are skipped unless SPLAT_EMU_FULL=1 (tests/conftest.py: EMU_ON_REQUEST).  The emulated
 library is test infrastructure; the product never loads it (tests/test_abi.py::test_no_cpu_fallback...)."""
 import os
 import sys
@@ -40,6 +41,8 @@ def emulated_device_memory(monkeypatch):
     monkeypatch.setattr(torch.cuda, "Stream", _fake_gpu.FakeStream)
     monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "device_count", lambda: 3)       # the emulated box: ordinals only
 
 
 # the GPU suite's functions, collected here against the emulated library (sizes the emulator finishes in seconds)
@@ -170,8 +173,8 @@ def _emu_rank_main(rank, world, port, mode, emu_path, q):
     log = _fake_gpu.install_emulated(setattr, emu_path, make_scene=bench.make_scene)
     lines = []
     _fake_gpu.quiet_bench(setattr, bench, sink=lines.append)
-    sys.argv = ["bench.py", "--gpus", str(world), "--gaussians", "3000", "--width", "160", "--height", "128", "--steps", "2", "--warmup", "3",
-                "--stripe-mode", mode]
+    sys.argv = ["bench.py", "--gpus", str(world), "--gaussians", "1500", "--width", "160", "--height", "128", "--steps", "2", "--warmup", "3",
+                "--stripe-mode", mode, "--rebalance-rounds", "1"]
     rc = bench.main()
     ctx = log.contexts[0]
     q.put({"rank": rank, "rc": rc, "lines": lines, "gathers": log.gathers, "sync_frames": ctx.kw.get("sync_frames")})
@@ -201,7 +204,7 @@ def test_bench_two_ranks_on_the_emulated_library(lib, orc, mode):
     _check_line(line, 2, 2, 3)
     assert r0["gathers"] == r1["gathers"] > 0
     assert r0["sync_frames"] == (1 if mode == "sync" else 0)
-    assert line["frame_checksum"] == _expected_checksum(orc, n=3000, W=160, H=128)
+    assert line["frame_checksum"] == _expected_checksum(orc, n=1500, W=160, H=128)
 
 
 def test_a_repeated_frame_is_counted_as_retried(lib):
@@ -220,3 +223,57 @@ def test_a_repeated_frame_is_counted_as_retried(lib):
     t = ctx.timings()
     assert t["frames_skipped"] == 1 and t["frames_retried"] == 1
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# multi-device code of the library on the emulated box ("devices" are ordinals, NCCL is tests/cuda_emu/fake_nccl.cpp)
+from test_gpu_multi import test_rank_contexts_gather_in_one_process  # noqa: E402,F401
+
+
+@pytest.mark.parametrize("equal", [True, False], ids=["equal_stripes", "rebalanced"])
+def test_group_context_equals_single_device_and_oracle_emulated(lib, orc, equal):
+    """tests/test_gpu_multi.py::test_group_context_equals_single_device_and_oracle at a size the emulator finishes
+    in seconds: splat_create_multi over three devices, scene broadcast, stripes rendered by the members, gathered,
+    re-cut from the members' measured times -- every frame equals the single-device frame and the oracle."""
+    import numpy as np
+
+    from test_gpu_multi import _camera
+
+    from splat_b200.gaussians import synthetic_scene
+
+    G, W, H = 3, 256, 160
+    scene = synthetic_scene(10_000, seed=0x5EED0081, log_scale_mean=-3.4)
+    grp = lib.Context(devices=list(range(G)), equal_stripes=equal)
+    grp.upload(scene)
+    one = lib.Context(device=0)
+    one.upload(scene)
+    cfg = orc.make_config()
+    rng = np.random.default_rng(81)
+    seen_bounds = set()
+    for k, yaw in enumerate(np.linspace(0.0, 1.2, 4)):
+        cam = _camera(W, H, (0.0, 0.0, 4.0), yaw=float(yaw))
+        fb0 = rng.integers(0, 2 ** 32, size=(H, W), dtype=np.uint64).astype(np.uint32) if k % 3 == 2 else np.zeros((H, W), np.uint32)
+        want = fb0.copy()
+        one.render(lib.camera_struct(cam), want)
+        got = fb0.copy()
+        grp.render(lib.camera_struct(cam), got)
+        assert np.array_equal(got, want), (k, int(np.count_nonzero(got != want)))
+        if k in (0, 2):
+            ref = fb0.copy()
+            orc.render(scene, orc.camera_from(cam), cfg, ref)
+            assert np.array_equal(got, ref)
+        got2 = np.full((H, W), 0xDEADBEEF, np.uint32)
+        grp.render_cleared(lib.camera_struct(cam), got2, 0)
+        want2 = np.zeros((H, W), np.uint32)
+        one.render(lib.camera_struct(cam), want2)
+        assert np.array_equal(got2, want2), k
+        seen_bounds.add(tuple(grp.group_bounds()))
+    b = grp.group_bounds()
+    assert b[0][0] == 0 and b[-1][1] == H and all(b[i][1] == b[i + 1][0] for i in range(G - 1))
+    if equal:
+        trows = [(r1 + 15) // 16 - r0 // 16 for r0, r1 in b]
+        assert max(trows) - min(trows) <= 1 and len(seen_bounds) == 1
+    t = grp.timings()
+    assert t["n_instances"] > 0 and t["n_gaussians"] == scene.num_gaussians
+    grp.close()
+    one.close()
