@@ -181,6 +181,16 @@ inline void yield() {           // back to the scheduler; returns when this fibe
   ctx_switch(f->ctx, w.sched);
 }
 
+// EMU_ORDER=random: besides the random order at barriers, a thread may lose its turn at any global load through
+// __ldg and at any atomic -- more interleavings of the threads of a block than barriers alone produce
+inline void maybe_yield() {
+  static const bool on = [] { const char *e = std::getenv("EMU_ORDER"); return e && std::strcmp(e, "random") == 0; }();
+  if (!on) return;
+  static thread_local unsigned long long r = 0xD1B54A32D192ED03ull;
+  r ^= r << 13; r ^= r >> 7; r ^= r << 17;
+  if ((r & 15u) == 0u && worker().cur) yield();
+}
+
 inline void release(Worker &w, Barrier &b) {
   b.count = 0;
   b.gen += 1;
@@ -244,10 +254,30 @@ inline void run_block(Worker &w, const cfg &c, unsigned long long b, int B, cons
     f.waits_on = nullptr;
     ctx_make(f.ctx, f.stack, FIBER_STACK, fiber_main);
   }
+  // order in which the runnable threads of a block get their turn: 0 = ascending (default), 1 = descending,
+  // 2 = a new random permutation every round (EMU_ORDER=reverse|random).  Code that relies on a barrier it does not
+  // have -- a shared-memory hand-over without __syncthreads, warp lockstep without __syncwarp -- works under at
+  // most one of the fixed orders.
+  static const int order_mode = [] {
+    const char *e = std::getenv("EMU_ORDER");
+    return !e ? 0 : (std::strcmp(e, "reverse") == 0 ? 1 : (std::strcmp(e, "random") == 0 ? 2 : 0));
+  }();
+  static thread_local std::vector<int> perm;
+  static thread_local unsigned long long rng = 0x9E3779B97F4A7C15ull ^ (unsigned long long)(uintptr_t)&perm;
+  if (order_mode) {
+    perm.resize((size_t)B);
+    for (int i = 0; i < B; ++i) perm[(size_t)i] = order_mode == 1 ? B - 1 - i : i;
+  }
   int done = 0;
   while (done < B) {
     bool ran = false;
-    for (int i = 0; i < B; ++i) {
+    if (order_mode == 2)
+      for (int i = B - 1; i > 0; --i) {
+        rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+        std::swap(perm[(size_t)i], perm[(size_t)(rng % (unsigned long long)(i + 1))]);
+      }
+    for (int ii = 0; ii < B; ++ii) {
+      const int i = order_mode ? perm[(size_t)ii] : ii;
       Fiber &f = w.fibers[i];
       if (f.st != READY) continue;
       ran = true;
@@ -482,7 +512,7 @@ T __shfl_xor_sync(unsigned, T v, int mask, int width = 32) {
 
 // ------------------------------------------------------------------------------------------------ atomics, loads, fences
 template <class T>
-T atomicAdd(T *p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL); }
+T atomicAdd(T *p, T v) { emu::maybe_yield(); return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL); }
 inline unsigned atomicAdd(unsigned *p, int v) { return __atomic_fetch_add(p, (unsigned)v, __ATOMIC_ACQ_REL); }
 inline float atomicAdd(float *p, float v) {
   std::atomic_ref<float> a(*p);
@@ -490,13 +520,13 @@ inline float atomicAdd(float *p, float v) {
   while (!a.compare_exchange_weak(old, old + v)) {}
   return old;
 }
-template <class T> T atomicMax(T *p, T v) { T old = __atomic_load_n(p, __ATOMIC_ACQUIRE); while (old < v && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) {} return old; }
+template <class T> T atomicMax(T *p, T v) { emu::maybe_yield(); T old = __atomic_load_n(p, __ATOMIC_ACQUIRE); while (old < v && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) {} return old; }
 template <class T> T atomicMin(T *p, T v) { T old = __atomic_load_n(p, __ATOMIC_ACQUIRE); while (old > v && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) {} return old; }
 template <class T> T atomicOr(T *p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_ACQ_REL); }
 template <class T> T atomicAnd(T *p, T v) { return __atomic_fetch_and(p, v, __ATOMIC_ACQ_REL); }
 template <class T> T atomicExch(T *p, T v) { return __atomic_exchange_n(p, v, __ATOMIC_ACQ_REL); }
-template <class T> T atomicCAS(T *p, T cmp, T v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE); return cmp; }
-template <class T> T __ldg(const T *p) { return *p; }
+template <class T> T atomicCAS(T *p, T cmp, T v) { emu::maybe_yield(); __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE); return cmp; }
+template <class T> T __ldg(const T *p) { emu::maybe_yield(); return *p; }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
