@@ -113,9 +113,32 @@ emu_switch:
   ret
 .size emu_switch,.-emu_switch
 )");
-struct Context { void *sp = nullptr; };
-inline void ctx_switch(Context &from, Context &to) { emu_switch(&from.sp, to.sp); }
+struct Context { void *sp = nullptr; const void *bottom = nullptr; size_t size = 0; };
+#if defined(__SANITIZE_ADDRESS__)
+// AddressSanitizer build (EMU_ASAN=1: out-of-bounds accesses of "device" and shared memory become reports): tell
+// the sanitizer about every stack switch.  `final`: the fiber being left will never run again.
+extern "C" void __sanitizer_start_switch_fiber(void **fake_stack_save, const void *bottom, size_t size);
+extern "C" void __sanitizer_finish_switch_fiber(void *fake_stack_save, const void **bottom_old, size_t *size_old);
+inline void ctx_switch(Context &from, Context &to, bool final = false) {
+  void *fake = nullptr;
+  __sanitizer_start_switch_fiber(final ? nullptr : &fake, to.bottom, to.size);
+  emu_switch(&from.sp, to.sp);
+  __sanitizer_finish_switch_fiber(fake, nullptr, nullptr);
+}
+inline void ctx_entered(Context &came_from) {        // first instruction of a new fiber: learn the scheduler's stack
+  const void *b = nullptr;
+  size_t n = 0;
+  __sanitizer_finish_switch_fiber(nullptr, &b, &n);
+  came_from.bottom = b;
+  came_from.size = n;
+}
+#else
+inline void ctx_switch(Context &from, Context &to, bool = false) { emu_switch(&from.sp, to.sp); }
+inline void ctx_entered(Context &) {}
+#endif
 inline void ctx_make(Context &c, void *stack, size_t size, void (*entry)()) {
+  c.bottom = stack;
+  c.size = size;
   uintptr_t top = (reinterpret_cast<uintptr_t>(stack) + size) & ~(uintptr_t)15;
   void **sp = reinterpret_cast<void **>(top);
   *--sp = nullptr;                                  // return address of entry (it never returns)
@@ -125,7 +148,8 @@ inline void ctx_make(Context &c, void *stack, size_t size, void (*entry)()) {
 }
 #else
 struct Context { ucontext_t uc; };
-inline void ctx_switch(Context &from, Context &to) { swapcontext(&from.uc, &to.uc); }
+inline void ctx_switch(Context &from, Context &to, bool = false) { swapcontext(&from.uc, &to.uc); }
+inline void ctx_entered(Context &) {}
 inline void ctx_make(Context &c, void *stack, size_t size, void (*entry)()) {
   getcontext(&c.uc);
   c.uc.uc_stack.ss_sp = stack;
@@ -207,6 +231,7 @@ inline void barrier_wait(Barrier &b, int expected) {
 }
 inline void fiber_main() {
   Worker &w = worker();
+  ctx_entered(w.sched);
   (*w.body)();
   // the thread has returned: it no longer takes part in any barrier of this block
   Fiber *f = w.cur;
@@ -217,7 +242,7 @@ inline void fiber_main() {
   w.live -= 1;
   if (w.bars[0].count > 0 && w.bars[0].count >= w.live) release(w, w.bars[0]);
   f->st = DONE;
-  ctx_switch(f->ctx, w.sched);
+  ctx_switch(f->ctx, w.sched, true);
   std::abort();   // a finished fiber is never resumed
 }
 
@@ -590,17 +615,60 @@ inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ?
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int d) { return d >= 0 && d < 64 ? cudaSuccess : cudaErrorInvalidValue; }   // "devices" are just ordinals
 inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+// EMU_GUARD=1: every "device" allocation ends 0..15 bytes before an inaccessible page and starts right after one,
+// so a kernel that reads or writes outside a buffer faults at the instruction that does it (a memcheck for global
+// memory at full speed).  Default: plain aligned allocations.
+namespace emu {
+struct GuardMap {
+  std::mutex m;
+  std::vector<std::tuple<void *, void *, size_t>> live;     // user pointer, mapping base, mapping length
+};
+inline GuardMap &guards() { static GuardMap *g = new GuardMap(); return *g; }
+inline bool guard_mode() { static const bool on = std::getenv("EMU_GUARD") != nullptr; return on; }
+inline void *guarded_alloc(size_t bytes) {
+  const size_t page = 4096, body = (bytes + 15) & ~(size_t)15, pages = (body + page - 1) / page + 2;
+  unsigned char *base = static_cast<unsigned char *>(mmap(nullptr, pages * page, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0));
+  if (base == MAP_FAILED) return nullptr;
+  mprotect(base, page, PROT_NONE);
+  mprotect(base + (pages - 1) * page, page, PROT_NONE);
+  unsigned char *user = base + (pages - 1) * page - body;
+  std::lock_guard<std::mutex> lk(guards().m);
+  guards().live.emplace_back(user, base, pages * page);
+  return user;
+}
+inline bool guarded_free(void *p) {
+  std::lock_guard<std::mutex> lk(guards().m);
+  auto &v = guards().live;
+  for (size_t i = 0; i < v.size(); ++i)
+    if (std::get<0>(v[i]) == p) {
+      munmap(std::get<1>(v[i]), std::get<2>(v[i]));
+      v[i] = v.back();
+      v.pop_back();
+      return true;
+    }
+  return false;
+}
+}  // namespace emu
 template <class T> cudaError_t cudaMalloc(T **p, size_t bytes) {
   void *q = nullptr;
-  if (posix_memalign(&q, 256, bytes ? bytes : 256)) return cudaErrorMemoryAllocation;
+  if (emu::guard_mode()) {
+    q = emu::guarded_alloc(bytes ? bytes : 16);
+    if (!q) return cudaErrorMemoryAllocation;
+  } else if (posix_memalign(&q, 256, bytes ? bytes : 256)) {
+    return cudaErrorMemoryAllocation;
+  }
   std::memset(q, 0xCD, bytes);                  // device memory is not zeroed: make reliance on that visible
   *p = static_cast<T *>(q);
   return cudaSuccess;
 }
-inline cudaError_t cudaFree(void *p) { std::free(p); return cudaSuccess; }
+inline cudaError_t cudaFree(void *p) {
+  if (p && emu::guard_mode() && emu::guarded_free(p)) return cudaSuccess;
+  std::free(p);
+  return cudaSuccess;
+}
 template <class T> cudaError_t cudaMallocHost(T **p, size_t bytes) { return cudaMalloc(p, bytes); }
 template <class T> cudaError_t cudaHostAlloc(T **p, size_t bytes, unsigned) { return cudaMalloc(p, bytes); }
-inline cudaError_t cudaFreeHost(void *p) { std::free(p); return cudaSuccess; }
+inline cudaError_t cudaFreeHost(void *p) { return cudaFree(p); }
 template <class T, class U> cudaError_t cudaHostGetDevicePointer(T **d, U *h, unsigned) { *d = reinterpret_cast<T *>(h); return cudaSuccess; }
 inline cudaError_t cudaHostRegister(void *, size_t, unsigned) { return cudaSuccess; }
 inline cudaError_t cudaHostUnregister(void *) { return cudaSuccess; }

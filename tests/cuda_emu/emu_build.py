@@ -180,7 +180,15 @@ def preprocess(name):
     return src
 
 
-def build(force=False):
+def build(force=False, asan=None):
+    """asan (default: env EMU_ASAN=1): AddressSanitizer build, _build/libsplat_b200_emu_asan.so; load it into a python that
+    runs with LD_PRELOAD=$(g++ -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0"""
+    asan = os.environ.get("EMU_ASAN") == "1" if asan is None else asan
+    out = OUT.replace(".so", "_asan.so") if asan else OUT
+    return _build(force, asan, out)
+
+
+def _build(force, asan, OUT):
     srcs = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh") or f == "splat_api.cu")
     deps = [os.path.join(CSRC, f) for f in srcs] + [os.path.join(HERE, f) for f in ("cuda_emu.h", "emu_build.py", "nccl.h", "cuda_runtime.h", "fake_nccl.cpp")]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
@@ -190,8 +198,11 @@ def build(force=False):
     for f in srcs:
         with open(os.path.join(gen, f.replace(".cu", ".cpp") if f.endswith(".cu") else f), "w") as o:
             o.write(f"// GENERATED by tests/cuda_emu/emu_build.py from splat_b200/csrc/{f} -- do not edit\n" + preprocess(f))
-    cmd = [os.environ.get("CXX", "g++"), "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-frounding-math",
-           "-fno-strict-aliasing", "-w", "-I", HERE, "-I", gen, "-o", OUT, os.path.join(gen, "splat_api.cpp"), "-ldl"]
+    cxx = os.environ.get("CXX", "g++")
+    if asan and os.path.exists("/usr/bin/g++"):
+        cxx = "/usr/bin/g++"                      # the distribution's compiler ships libasan
+    cmd = [cxx, "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-frounding-math",
+           "-fno-strict-aliasing", "-w", *(["-fsanitize=address", "-fno-omit-frame-pointer"] if asan else []), "-I", HERE, "-I", gen, "-o", OUT, os.path.join(gen, "splat_api.cpp"), "-ldl"]
     subprocess.check_call(cmd)
     subprocess.check_call([os.environ.get("CXX", "g++"), "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-I", HERE,
                            "-o", NCCL, os.path.join(HERE, "fake_nccl.cpp")])
