@@ -168,7 +168,11 @@ struct Fiber {
   void *stack = nullptr;
 };
 
+#if defined(__SANITIZE_ADDRESS__)
+constexpr size_t FIBER_STACK = 64u << 10;    // the sanitizer touches the shadow of a whole stack at every fiber start
+#else
 constexpr size_t FIBER_STACK = 256u << 10;
+#endif
 
 struct Worker {                 // one per OS thread; runs one block at a time
   std::vector<Fiber> fibers;

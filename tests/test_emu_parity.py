@@ -277,3 +277,48 @@ def test_group_context_equals_single_device_and_oracle_emulated(lib, orc, equal)
     assert t["n_instances"] > 0 and t["n_gaussians"] == scene.num_gaussians
     grp.close()
     one.close()
+
+
+def test_stripe_harness_repeats_an_abandoned_frame_locally(lib, orc):
+    """stripes.render_with_retry / timings_with_retry (what bench.py's ranks use) against the REAL retry contract of
+    splat_render_device: a stripe frame that outgrows its launch bounds is abandoned on the device, the next call on
+    that context reports SPLAT_ERR_RETRY once, the helper renders the abandoned frame again and carries on -- and
+    every frame a rank ends up with equals the oracle's rows."""
+    import numpy as np
+
+    from test_gpu_parity import _camera, _scene
+
+    from splat_b200 import stripes
+
+    W, H = 320, 208
+    scene = _scene(40_000, 0x5EED0072, -3.4)
+    cams = [_camera(W, H, (0.0, 0.0, z)) for z in (40.0, 40.0, 1.5, 1.6)]      # the third frame wants > 10x the instances
+    cfg = orc.make_config()
+    want = []
+    for cam in cams:
+        ref = np.zeros((H, W), np.uint32)
+        orc.render(scene, orc.camera_from(cam), cfg, ref)
+        want.append(ref)
+    bounds = [(0, 96), (96, 208)]
+    repeated = 0
+    for r0, r1 in bounds:
+        ctx = lib.Context(device=0, near_cut=0, max_instances=1)
+        ctx.upload(scene)
+        fb = np.zeros((H, W), np.uint32)
+
+        def render(i):
+            fb[r0:r1] = 0
+            ctx.render_device(lib.camera_struct(cams[i]), fb[r0:r1].ctypes.data, W, H, r0, r1)
+
+        def is_retry(e):
+            return isinstance(e, lib.SplatError) and e.code == stripes.RETRY
+
+        for i in range(len(cams)):
+            repeated += stripes.render_with_retry(render, i, is_retry)
+            if i == len(cams) - 1 or i == 1:
+                _, rep = stripes.timings_with_retry(ctx.timings, render, i, is_retry)     # waits for frame i (repeats it if abandoned)
+                repeated += rep
+                assert np.array_equal(fb[r0:r1], want[i][r0:r1]), (r0, i, int(np.count_nonzero(fb[r0:r1] != want[i][r0:r1])))
+        assert ctx.timings()["frames_skipped"] >= 1
+        ctx.close()
+    assert repeated >= 2                                                         # each stripe had its near frame abandoned once
