@@ -455,7 +455,18 @@ class Device {
   }
   Device(const Device &) = delete;
   Device &operator=(const Device &) = delete;
-  ~Device() { if (ctx_) splat_destroy(ctx_); }
+  ~Device() {
+    if (pinned_) splat_unpin_host(pinned_);
+    if (ctx_) splat_destroy(ctx_);
+  }
+  // pin the caller's colour buffer once (cudaHostRegister) so that the per-frame copies of splat_render run at
+  // full PCIe rate; pinned again when the buffer was re-allocated.  Failure to pin is not an error.
+  void pin(void *p, size_t bytes) {
+    if (p == pinned_ && bytes == pinned_bytes_) return;
+    if (pinned_) splat_unpin_host(pinned_);
+    pinned_ = splat_pin_host(p, bytes) == SPLAT_OK ? p : nullptr;
+    pinned_bytes_ = pinned_ ? bytes : 0;
+  }
 
   splat_ctx *ctx() { return ctx_; }
   void check(int rc, const char *what) {
@@ -476,6 +487,8 @@ class Device {
   const void *scene_ptr_ = nullptr;
   size_t scene_len_ = 0;
   bool valid_ = false;
+  void *pinned_ = nullptr;
+  size_t pinned_bytes_ = 0;
 };
 
 // GaussianSplatPipeline01, pipelines.rs:54-169: `gaussians: Vec<Gaussian>`, low-pass +0.01 (gaussians.rs:156-157)
@@ -495,6 +508,7 @@ class GaussianSplatPipeline01 {
     }
     const splat_camera cam = camera_struct(camera);
     const auto sz = color.size();
+    dev_.pin(color.raw_mut(), sz[0] * sz[1] * sizeof(uint32_t));
     dev_.check(splat_render(dev_.ctx(), &cam, color.raw_mut(), (uint32_t)sz[0], (uint32_t)sz[1]), "splat_render");
   }
   void scene_changed() { dev_.invalidate(); }   // after mutating `gaussians` in place
@@ -517,6 +531,7 @@ class GaussianSplatPipeline02 {
     upload_if_needed();
     const splat_camera cam = camera_struct(camera);
     const auto sz = color.size();
+    dev_.pin(color.raw_mut(), sz[0] * sz[1] * sizeof(uint32_t));
     dev_.check(splat_render(dev_.ctx(), &cam, color.raw_mut(), (uint32_t)sz[0], (uint32_t)sz[1]), "splat_render");
   }
   // `color.fill(clear); render_to_buffer(&mut color)` (main.rs:73-74) in one call: no host fill, no upload of it
@@ -524,6 +539,7 @@ class GaussianSplatPipeline02 {
     upload_if_needed();
     const splat_camera cam = camera_struct(camera);
     const auto sz = color.size();
+    dev_.pin(color.raw_mut(), sz[0] * sz[1] * sizeof(uint32_t));
     dev_.check(splat_render_cleared(dev_.ctx(), &cam, color.raw_mut(), (uint32_t)sz[0], (uint32_t)sz[1], clear), "splat_render_cleared");
   }
   void scene_changed() { dev_.invalidate(); }

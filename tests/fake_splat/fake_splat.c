@@ -24,6 +24,7 @@ struct splat_ctx {
 };
 
 static char g_create_error[256] = "";
+static int g_pins = 0, g_pins_total = 0;
 
 uint32_t splat_abi_version(void) { return SPLAT_ABI_VERSION; }
 void splat_config_default(splat_config *c) {
@@ -48,7 +49,7 @@ const char *splat_create_error(void) { return g_create_error; }
 void splat_destroy(splat_ctx *c) {
   if (!c) return;
   const char *log = getenv("FAKE_SPLAT_LOG");
-  if (log) { FILE *f = fopen(log, "a"); if (f) { fprintf(f, "uploads=%d renders=%d lowpass=%.2f\n", c->uploads, c->renders, c->cfg.lowpass); fclose(f); } }
+  if (log) { FILE *f = fopen(log, "a"); if (f) { fprintf(f, "uploads=%d renders=%d lowpass=%.2f pinned=%d still=%d\n", c->uploads, c->renders, c->cfg.lowpass, g_pins_total, g_pins); fclose(f); } }
   free(c->pos4); free(c->cov); free(c->op); free(c->sh); free(c);
 }
 const char *splat_last_error(const splat_ctx *c) { return c ? c->err : "null context"; }
@@ -96,6 +97,8 @@ int splat_render_cleared(splat_ctx *c, const splat_camera *cam, uint32_t *fb, ui
   for (uint64_t i = 0; i < (uint64_t)W * H; ++i) fb[i] = clear;
   return splat_render(c, cam, fb, W, H);
 }
+int splat_pin_host(void *p, uint64_t bytes) { (void)bytes; if (!p) return SPLAT_ERR_INVALID; g_pins += 1; g_pins_total += 1; return SPLAT_OK; }
+int splat_unpin_host(void *p) { (void)p; g_pins -= 1; return SPLAT_OK; }
 int splat_get_timings(splat_ctx *c, splat_timings *t) {
   if (!c || !t) return SPLAT_ERR_INVALID;
   memset(t, 0, sizeof *t);

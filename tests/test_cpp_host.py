@@ -181,14 +181,14 @@ def test_render_loop_hands_the_library_exactly_the_right_bytes(demo, tmp_path, o
         assert np.array_equal(fb, ref), f"{np.count_nonzero(fb != ref)} pixels differ"
         seen.add(fb.tobytes())
     assert len(seen) == frames                                              # the camera really moved
-    assert log.read_text().strip() == f"uploads=1 renders={frames} lowpass={lowpass:.2f}"
+    assert log.read_text().strip() == f"uploads=1 renders={frames} lowpass={lowpass:.2f} pinned=1 still=0"   # the colour buffer: pinned once, unpinned before destroy
 
 
 def test_listing_devices_asks_for_a_group_context(demo, tmp_path, fake_lib_dir):
     log = tmp_path / "fake.log"
     env = {"LD_LIBRARY_PATH": fake_lib_dir + ":" + os.path.join(ROOT, "oracle"), "FAKE_SPLAT_LOG": str(log), "SPLAT_DEMO_DEVICES": "0,2,3"}
     run(demo, "render", "naive", 96, 160, 0, 0, 5, 2, 0.1, 2, 0, tmp_path / "o.bin", env=env)
-    assert log.read_text().splitlines() == ["group of 3: 0 2 3", "uploads=1 renders=2 lowpass=0.30"]
+    assert log.read_text().splitlines() == ["group of 3: 0 2 3", "uploads=1 renders=2 lowpass=0.30 pinned=1 still=0"]
 
 
 def test_library_errors_surface_as_exceptions_with_the_library_message(demo, tmp_path, fake_lib_dir):
