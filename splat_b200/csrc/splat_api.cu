@@ -1679,9 +1679,18 @@ int splat_group_get_bounds(splat_ctx *c, uint32_t *bounds, int32_t cap_ranks, in
   return SPLAT_OK;
 }
 
+// (a refused registration is not sticky, but it would be the "last error" the next frame's launch check reads)
 int splat_pin_host(void *p, uint64_t bytes) {
-  return cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess ? SPLAT_OK : SPLAT_ERR_CUDA;
+  if (!p || bytes == 0) return SPLAT_ERR_INVALID;
+  if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) return SPLAT_OK;
+  (void)cudaGetLastError();
+  return SPLAT_ERR_CUDA;
 }
-int splat_unpin_host(void *p) { return cudaHostUnregister(p) == cudaSuccess ? SPLAT_OK : SPLAT_ERR_CUDA; }
+int splat_unpin_host(void *p) {
+  if (!p) return SPLAT_ERR_INVALID;
+  if (cudaHostUnregister(p) == cudaSuccess) return SPLAT_OK;
+  (void)cudaGetLastError();
+  return SPLAT_ERR_CUDA;
+}
 
 }  // extern "C"
