@@ -148,7 +148,9 @@ const char *splat_last_error(const splat_ctx *ctx);
  * the contiguous column-major nalgebra matrix -- pos4 4xN (x,y,z,1), scale3 3xN (already
  * exp'd), opacity N (already sigmoid'd), rot_xyzw 4xN (nalgebra coords order i,j,k,w,
  * un-normalised is fine), sh48 48xN.  Host pointers.  Copies to the device, computes cov3d
- * there (compute_cov3d, gaussians.rs:446-462) and repacks to the device layout. */
+ * there (compute_cov3d, gaussians.rs:446-462) and repacks to the device layout.
+ * n = 0 (every upload call) is a valid, empty scene: its frames check their arguments and draw nothing, like
+ * render_to_buffer over an empty Vec<Gaussian>. */
 int splat_upload_soa(splat_ctx *ctx, const float *pos4, const float *scale3, const float *opacity,
                      const float *rot_xyzw, const float *sh48, uint64_t n);
 

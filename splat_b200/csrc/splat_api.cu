@@ -112,6 +112,7 @@ struct splat_ctx {
   uint32_t *last_fb = nullptr;
   cudaStream_t last_stream = nullptr;
   uint32_t retried = 0;
+  bool empty_scene = false;         // an upload of zero Gaussians: a valid scene that renders nothing (the reference's empty Vec)
   uint64_t launches = 0, last_instances = 0, last_visible = 0, last_tiles = 0, last_sort = 0;
 
   // ---- multi-GPU (comm.cuh).  One process per GPU: this context joined a communicator
@@ -265,6 +266,7 @@ void free_scene(splat_ctx *c) {
 int alloc_scene(splat_ctx *c, uint64_t n) {
   if (n == 0 || n > 0x7FFFFFFFull) return fail(c, SPLAT_ERR_INVALID, "n must be in [1, 2^31)");
   free_scene(c);
+  c->empty_scene = false;
   CU(dev_alloc(&c->scene, (size_t)SCENE_PLANES * n));
   CU(dev_alloc(&c->recs, n));
   CU(dev_alloc(&c->rects, n));
@@ -809,6 +811,21 @@ int finish_frame(splat_ctx *c) {
   return SPLAT_OK;
 }
 
+// An empty scene (an empty Vec<Gaussian> / a PLY with no vertices) is valid input for render_to_buffer: nothing is drawn.
+// No device memory, no kernel: the render entry points return before touching the device.
+int upload_empty(splat_ctx *c) {
+  CU(cudaSetDevice(c->cfg.device));
+  CU(cudaStreamSynchronize(c->stream));
+  free_scene(c);
+  c->n = 0;
+  c->empty_scene = true;
+  for (splat_ctx *m : c->members) {
+    int rc = upload_empty(m);
+    if (rc) { c->err = m->err; return rc; }
+  }
+  return SPLAT_OK;
+}
+
 int upload_common(splat_ctx *c, uint64_t n) {
   CU(cudaSetDevice(c->cfg.device));
   return alloc_scene(c, n);
@@ -1160,6 +1177,7 @@ const char *splat_last_error(const splat_ctx *c) { return c ? c->err.c_str() : "
 int splat_upload_soa(splat_ctx *c, const float *pos4, const float *scale3, const float *opacity,
                      const float *rot_xyzw, const float *sh48, uint64_t n) {
   if (!c) return SPLAT_ERR_INVALID;
+  if (n == 0) return upload_empty(c);
   if (!c->members.empty()) {
     int rc = splat_upload_soa(c->members[0], pos4, scale3, opacity, rot_xyzw, sh48, n);
     if (rc) { c->err = c->members[0]->err; return rc; }
@@ -1190,6 +1208,7 @@ int splat_upload_soa(splat_ctx *c, const float *pos4, const float *scale3, const
 
 int splat_upload_ply_raw(splat_ctx *c, const void *vertex_rows, uint64_t n, uint32_t stride_floats, float *activated60) {
   if (!c) return SPLAT_ERR_INVALID;
+  if (n == 0) return upload_empty(c);
   if (!vertex_rows) return fail(c, SPLAT_ERR_INVALID, "null vertex payload");
   if (stride_floats < (uint32_t)PLY_FLOATS) return fail(c, SPLAT_ERR_INVALID, "the INRIA vertex layout has 62 floats per vertex");
   if (!c->members.empty()) {
@@ -1223,6 +1242,7 @@ int splat_upload_ply_raw(splat_ctx *c, const void *vertex_rows, uint64_t n, uint
 
 int splat_upload_aos(splat_ctx *c, const float *g59, uint64_t n) {
   if (!c) return SPLAT_ERR_INVALID;
+  if (n == 0) return upload_empty(c);
   if (!c->members.empty()) {
     int rc = splat_upload_aos(c->members[0], g59, n);
     if (rc) { c->err = c->members[0]->err; return rc; }
@@ -1244,6 +1264,18 @@ int splat_upload_aos(splat_ctx *c, const float *g59, uint64_t n) {
   return SPLAT_OK;
 }
 
+// a frame of an EMPTY scene: the arguments are checked like those of any frame, nothing is drawn.  clear < 0: the
+// target keeps its contents (render_to_buffer blends onto it); otherwise the host target is filled with `clear`.
+static int render_nothing(splat_ctx *c, const splat_camera *cam, uint32_t *host_fb, uint32_t W, uint32_t H, uint32_t row0, uint32_t row1,
+                          long long clear) {
+  splat_ctx *m = c->members.empty() ? c : c->members[0];
+  FrameParams P;
+  const int rc = make_params(m, cam, W, H, row0, row1, &P);
+  if (rc) { c->err = m->err; return rc; }
+  if (host_fb && clear >= 0) std::fill(host_fb, host_fb + (size_t)(row1 - row0) * W, (uint32_t)clear);
+  return SPLAT_OK;
+}
+
 // a frame skipped on the device cannot be repeated behind the caller's back when the target is the
 // caller's device buffer (it may already have been consumed): report it, once, on the next call
 static int report_skipped(splat_ctx *c) {
@@ -1260,6 +1292,7 @@ int splat_render_device(splat_ctx *c, const splat_camera *cam, void *fb_rows_dev
                         uint32_t row0, uint32_t row1, void *stream) {
   if (!c) return SPLAT_ERR_INVALID;
   if (!c->members.empty()) return fail(c, SPLAT_ERR_UNSUPPORTED, "a group context renders through the host-buffer entry points");
+  if (c->empty_scene) return fb_rows_dev ? render_nothing(c, cam, nullptr, W, H, row0, row1, -1) : fail(c, SPLAT_ERR_INVALID, "framebuffer is null");
   if (!c->n) return fail(c, SPLAT_ERR_STATE, "no scene uploaded");
   if (!fb_rows_dev) return fail(c, SPLAT_ERR_INVALID, "framebuffer is null");
   FrameParams P;
@@ -1299,6 +1332,7 @@ static int host_frame(splat_ctx *c, const FrameParams &P, uint32_t *host_fb, siz
 int splat_render_rows(splat_ctx *c, const splat_camera *cam, uint32_t *fb_rows, uint32_t W, uint32_t H,
                       uint32_t row0, uint32_t row1) {
   if (!c) return SPLAT_ERR_INVALID;
+  if (c->empty_scene) return fb_rows ? render_nothing(c, cam, fb_rows, W, H, row0, row1, -1) : fail(c, SPLAT_ERR_INVALID, "framebuffer is null");
   if (!c->members.empty()) {
     if (row0 != 0 || row1 != H) return fail(c, SPLAT_ERR_UNSUPPORTED, "a group context renders whole frames (it cuts the stripes itself)");
     return group_render(c, cam, fb_rows, W, H, -1);
@@ -1341,6 +1375,7 @@ int splat_render(splat_ctx *c, const splat_camera *cam, uint32_t *fb, uint32_t W
 int splat_render_cleared(splat_ctx *c, const splat_camera *cam, uint32_t *fb_out, uint32_t W, uint32_t H,
                          uint32_t clear) {
   if (!c) return SPLAT_ERR_INVALID;
+  if (c->empty_scene) return fb_out ? render_nothing(c, cam, fb_out, W, H, 0, H, (long long)clear) : fail(c, SPLAT_ERR_INVALID, "framebuffer is null");
   if (!c->members.empty()) return group_render(c, cam, fb_out, W, H, (long long)clear);
   if (!c->n) return fail(c, SPLAT_ERR_STATE, "no scene uploaded");
   if (!fb_out) return fail(c, SPLAT_ERR_INVALID, "framebuffer is null");
@@ -1396,6 +1431,7 @@ int splat_debug_render_float(splat_ctx *c, const splat_camera *cam, uint32_t *fb
 
 int splat_get_timings(splat_ctx *c, splat_timings *t) {
   if (!c || !t) return SPLAT_ERR_INVALID;
+  if (c->empty_scene) { std::memset(t, 0, sizeof(*t)); return SPLAT_OK; }     // frames of an empty scene do no work
   if (!c->members.empty()) {
     if (!c->have_frame) return fail(c, SPLAT_ERR_STATE, "no frame rendered yet");
     return group_timings(c, t);

@@ -65,11 +65,11 @@ static int store(splat_ctx *c, const float *pos4, const float *scale3, const flo
   return SPLAT_OK;
 }
 int splat_upload_soa(splat_ctx *c, const float *pos4, const float *scale3, const float *opacity, const float *rot_xyzw, const float *sh48, uint64_t n) {
-  if (!c || !pos4 || !scale3 || !opacity || !rot_xyzw || !sh48) return SPLAT_ERR_INVALID;
+  if (!c || (n && (!pos4 || !scale3 || !opacity || !rot_xyzw || !sh48))) return SPLAT_ERR_INVALID;   /* n = 0: an empty scene */
   return store(c, pos4, scale3, opacity, rot_xyzw, sh48, n);
 }
 int splat_upload_aos(splat_ctx *c, const float *g59, uint64_t n) {
-  if (!c || !g59) return SPLAT_ERR_INVALID;
+  if (!c || (n && !g59)) return SPLAT_ERR_INVALID;
   const uint64_t m = n ? n : 1;
   float *pos = (float *)malloc(m * 16), *sc = (float *)malloc(m * 12), *op = (float *)malloc(m * 4), *rot = (float *)malloc(m * 16), *sh = (float *)malloc(m * 192);
   for (uint64_t i = 0; i < n; ++i) {

@@ -184,6 +184,20 @@ def test_render_loop_hands_the_library_exactly_the_right_bytes(demo, tmp_path, o
     assert log.read_text().strip() == f"uploads=1 renders={frames} lowpass={lowpass:.2f} pinned=1 still=0"   # the colour buffer: pinned once, unpinned before destroy
 
 
+def test_a_ply_without_vertices_is_an_empty_scene(demo, tmp_path, fake_lib_dir):
+    """load_from_ply on `element vertex 0` gives an empty Vec (no division by zero in the recentring), and
+    render_to_buffer over it leaves the cleared buffer cleared"""
+    W, H = 64, 48
+    ply, dump, out = tmp_path / "e.ply", tmp_path / "e.bin", tmp_path / "f.bin"
+    save_ply(str(ply), {"x": np.zeros(0, np.float32)})
+    run(demo, "ply", ply, dump)
+    assert read_list(dump).num_gaussians == 0
+    env = {"LD_LIBRARY_PATH": fake_lib_dir + ":" + os.path.join(ROOT, "oracle")}
+    run(demo, "render", ply, H, W, 0.0, 0.0, 3.0, 2, 0.2, 2, 0, out, env=env)
+    for _, fb in read_frames(out, W, H):
+        assert not fb.any()
+
+
 def test_listing_devices_asks_for_a_group_context(demo, tmp_path, fake_lib_dir):
     log = tmp_path / "fake.log"
     env = {"LD_LIBRARY_PATH": fake_lib_dir + ":" + os.path.join(ROOT, "oracle"), "FAKE_SPLAT_LOG": str(log), "SPLAT_DEMO_DEVICES": "0,2,3"}

@@ -55,6 +55,7 @@ from test_gpu_parity import (  # noqa: E402,F401
     test_blends_onto_existing_contents,
     test_degenerate_inputs_are_skipped,
     test_depth_order_matches_stable_sort,
+    test_empty_scene_renders_nothing,
     test_errors_not_crashes,
     test_euc_switches,
     test_frames_without_a_host_round_trip,
@@ -327,3 +328,20 @@ def test_stripe_harness_repeats_an_abandoned_frame_locally(lib, orc):
         assert ctx.timings()["frames_skipped"] >= 1
         ctx.close()
     assert repeated >= 2                                                         # each stripe had its near frame abandoned once
+
+
+def test_cpp_host_renders_an_empty_ply_on_the_emulated_library(lib, cpp_demo, tmp_path):
+    import numpy as np
+
+    from test_cpp_host import read_frames, run
+
+    from splat_b200.gaussians import save_ply
+
+    libdir = tmp_path / "lib"
+    libdir.mkdir()
+    os.symlink(lib.LIB_PATH, libdir / "libsplat_b200.so")
+    ply, out = tmp_path / "e.ply", tmp_path / "f.bin"
+    save_ply(str(ply), {"x": np.zeros(0, np.float32)})
+    for which in (1, 2):
+        run(cpp_demo, "render", ply, 48, 64, 0.0, 0.0, 3.0, 2, 0.2, which, 0, out, env={"LD_LIBRARY_PATH": str(libdir)})
+        assert all(not fb.any() for _, fb in read_frames(out, 64, 48))
