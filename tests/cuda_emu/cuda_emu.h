@@ -192,6 +192,7 @@ inline Worker &worker() { static thread_local Worker w; return w; }
 inline dim3 &block_dim() { static dim3 d; return d; }
 inline dim3 &grid_dim() { static dim3 d; return d; }
 inline Thread &self() { return worker().cur->t; }
+inline int &last_error() { static int e = 0; return e; }
 inline std::mutex &launch_mutex() { static std::mutex m; return m; }   // one launch at a time, process-wide
 
 struct cfg {
@@ -382,7 +383,13 @@ void run_grid(const cfg &c, Body body_fn, const char *name = "") {
   const auto t_start = std::chrono::steady_clock::now();
   const int B = (int)(c.block.x * c.block.y * c.block.z);
   const unsigned long long G = (unsigned long long)c.grid.x * c.grid.y * c.grid.z;
-  if (B <= 0 || G == 0) return;
+  if (B <= 0 || B > 1024 || G == 0 || c.grid.x > 0x7FFFFFFFu || c.grid.y > 65535u || c.grid.z > 65535u || c.smem > 227u * 1024u) {
+    // what the runtime answers with cudaErrorInvalidConfiguration: a launch that silently did nothing here would hide it
+    std::fprintf(stderr, "cuda_emu: invalid launch configuration for %s: grid (%u,%u,%u) block (%u,%u,%u) smem %zu\n", name, c.grid.x, c.grid.y,
+                 c.grid.z, c.block.x, c.block.y, c.block.z, c.smem);
+    last_error() = 9;   // cudaErrorInvalidConfiguration
+    return;
+  }
   block_dim() = c.block;
   grid_dim() = c.grid;
   const std::function<void()> body = body_fn;
@@ -615,8 +622,8 @@ typedef emu_event *cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocMapped = 2, cudaHostRegisterDefault = 0 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
-inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : (e == cudaErrorMemoryAllocation ? "out of memory" : "emulated CUDA error"); }
-inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : e == 9 ? "invalid configuration argument" : (e == cudaErrorMemoryAllocation ? "out of memory" : "emulated CUDA error"); }
+inline cudaError_t cudaGetLastError() { const int e = emu::last_error(); emu::last_error() = 0; return e; }
 inline cudaError_t cudaSetDevice(int d) { return d >= 0 && d < 64 ? cudaSuccess : cudaErrorInvalidValue; }   // "devices" are just ordinals
 inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 // EMU_GUARD=1: every "device" allocation ends 0..15 bytes before an inaccessible page and starts right after one,

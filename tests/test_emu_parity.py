@@ -57,6 +57,7 @@ from test_gpu_parity import (  # noqa: E402,F401
     test_depth_order_matches_stable_sort,
     test_empty_scene_renders_nothing,
     test_errors_not_crashes,
+    test_everything_culled_leaves_the_buffer_untouched,
     test_euc_switches,
     test_frames_without_a_host_round_trip,
     test_near_cut_is_exact,

@@ -523,6 +523,32 @@ def test_empty_scene_renders_nothing(lib, orc):
     ctx.close()
 
 
+@pytest.mark.parametrize("near_cut,sync_frames", [(0, 0), (-1, 0), (64, 0), (0, 1)])
+def test_everything_culled_leaves_the_buffer_untouched(lib, orc, near_cut, sync_frames):
+    """A scene entirely behind the camera: no visible Gaussian, no tile instance, on the first frame of a geometry
+    and on the frames after it (launches sized from a count of zero), whole frames and stripes."""
+    W, H = 200, 120
+    scene = _scene(3000, 0x5EED0096, -3.0)
+    scene.positions[:, 2] += 20.0
+    noise = np.random.default_rng(1).integers(0, 2 ** 32, size=(H, W), dtype=np.uint64).astype(np.uint32)
+    ctx = lib.Context(device=0, near_cut=near_cut, sync_frames=sync_frames)
+    ctx.upload(scene)
+    for k in range(3):
+        cam = _camera(W, H, (0.0, 0.0, 5.0), yaw=0.1 * k)
+        ref = noise.copy()
+        st = orc.render(scene, orc.camera_from(cam), orc.make_config(), ref)
+        assert st.n_visible == 0 and np.array_equal(ref, noise)
+        fb = noise.copy()
+        ctx.render(lib.camera_struct(cam), fb)
+        assert np.array_equal(fb, noise)
+        t = ctx.timings()
+        assert t["n_visible"] == 0 and t["n_instances"] == 0
+        part = np.ascontiguousarray(noise[32:64])
+        ctx.render(lib.camera_struct(cam), part, 32, 64)
+        assert np.array_equal(part, noise[32:64])
+    ctx.close()
+
+
 def test_render_cleared_equals_fill_then_render(lib, orc):
     """splat_render_cleared == Buffer2d::fill(clear) + render_to_buffer (main.rs:73-74), for a
     byte-uniform and a general clear value, whatever the output buffer held before."""
