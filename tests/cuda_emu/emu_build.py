@@ -185,10 +185,13 @@ def build(force=False, asan=None):
     runs with LD_PRELOAD=$(g++ -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0"""
     asan = os.environ.get("EMU_ASAN") == "1" if asan is None else asan
     out = OUT.replace(".so", "_asan.so") if asan else OUT
-    return _build(force, asan, out)
+    defines = os.environ.get("EMU_DEFINES", "").split()        # e.g. EMU_DEFINES="-DSPLAT_TMA_STAGE=1": a compile-time variant
+    if defines:
+        out = out.replace(".so", "_" + "".join(ch if ch.isalnum() else "_" for ch in " ".join(defines)) + ".so")
+    return _build(force, asan, out, defines)
 
 
-def _build(force, asan, OUT):
+def _build(force, asan, OUT, defines=()):
     srcs = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh") or f == "splat_api.cu")
     deps = [os.path.join(CSRC, f) for f in srcs] + [os.path.join(HERE, f) for f in ("cuda_emu.h", "emu_build.py", "nccl.h", "cuda_runtime.h", "fake_nccl.cpp")]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
@@ -202,7 +205,7 @@ def _build(force, asan, OUT):
     if asan and os.path.exists("/usr/bin/g++"):
         cxx = "/usr/bin/g++"                      # the distribution's compiler ships libasan
     cmd = [cxx, "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-frounding-math",
-           "-fno-strict-aliasing", "-w", *(["-fsanitize=address", "-fno-omit-frame-pointer"] if asan else []), "-I", HERE, "-I", gen, "-o", OUT, os.path.join(gen, "splat_api.cpp"), "-ldl"]
+           "-fno-strict-aliasing", "-w", *(["-fsanitize=address", "-fno-omit-frame-pointer"] if asan else []), *defines, "-I", HERE, "-I", gen, "-o", OUT, os.path.join(gen, "splat_api.cpp"), "-ldl"]
     subprocess.check_call(cmd)
     subprocess.check_call([os.environ.get("CXX", "g++"), "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-I", HERE,
                            "-o", NCCL, os.path.join(HERE, "fake_nccl.cpp")])
