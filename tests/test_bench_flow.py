@@ -113,10 +113,15 @@ def test_two_rank_flow_gathers_once_per_frame_whatever_happens_to_a_rank(mode, o
     procs = [mpc.Process(target=_rank_main, args=(r, 2, port, mode, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted((q.get(timeout=300) for _ in procs), key=lambda r: r["rank"])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    try:
+        res = sorted((q.get(timeout=300) for _ in procs), key=lambda r: r["rank"])
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:            # never leave a rank behind, whatever happened
+            if p.is_alive():
+                p.kill()
     r0, r1 = res
     assert r0["rc"] == 0 and r1["rc"] == 0
     assert len(r0["lines"]) == 1 and r1["lines"] == []         # rank 0 alone prints, one line

@@ -201,10 +201,15 @@ def test_bench_two_ranks_on_the_emulated_library(lib, orc, mode):
     procs = [mpc.Process(target=_emu_rank_main, args=(r, 2, port, mode, lib.LIB_PATH, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted((q.get(timeout=900) for _ in procs), key=lambda r: r["rank"])
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    try:
+        res = sorted((q.get(timeout=900) for _ in procs), key=lambda r: r["rank"])
+        for p in procs:
+            p.join(timeout=120)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:            # never leave a rank behind, whatever happened
+            if p.is_alive():
+                p.kill()
     r0, r1 = res
     assert r0["rc"] == 0 and r1["rc"] == 0 and len(r0["lines"]) == 1 and r1["lines"] == []
     line = r0["lines"][0]

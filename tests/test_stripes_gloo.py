@@ -127,10 +127,15 @@ def test_world_size_2_gather_equals_full_frame(balanced):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, balanced, q)) for r in range(2)]
     for p in procs:
         p.start()
-    ok, bad, bounds = q.get(timeout=240)
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    try:
+        ok, bad, bounds = q.get(timeout=240)
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:
+            if p.is_alive():
+                p.kill()
     assert ok, f"{bad} pixels differ after the gather (bounds {bounds})"
     assert bounds[0][1] == bounds[1][0] and bounds[1][1] == 150
 
