@@ -22,6 +22,7 @@ EMU_ON_REQUEST = (
     "test_deep_lists_exact_early_termination[deep_150k_128x96]", "test_deep_lists_exact_early_termination[deep_mixed_opacity]",
     "test_deep_lists_exact_early_termination[deep_onto_noise]", "test_bench_two_ranks_on_the_emulated_library[async]",
     "test_group_context_equals_single_device_and_oracle_emulated[equal_stripes]",
+    "test_group_context_repeats_abandoned_member_stripes",
     "test_cpp_viewer_loop_on_the_emulated_library[2-1-3000-320-240]", "test_cpp_viewer_loop_on_the_emulated_library[1-0-1500-200-150]",
 )
 

@@ -351,3 +351,34 @@ def test_cpp_host_renders_an_empty_ply_on_the_emulated_library(lib, cpp_demo, tm
     for which in (1, 2):
         run(cpp_demo, "render", ply, 48, 64, 0.0, 0.0, 3.0, 2, 0.2, which, 0, out, env={"LD_LIBRARY_PATH": str(libdir)})
         assert all(not fb.any() for _, fb in read_frames(out, 64, 48))
+
+
+def test_group_context_repeats_abandoned_member_stripes(lib, orc):
+    """a camera that jumps from far to near: the members' stripes outgrow their launch bounds, are abandoned on the
+    "device" and repeated inside splat_render of the group -- frames blended onto noise and the fused clear stay exact"""
+    import numpy as np
+
+    from test_gpu_multi import _camera
+
+    from splat_b200.gaussians import synthetic_scene
+
+    W, H = 320, 208
+    scene = synthetic_scene(40_000, seed=0x5EED0072, log_scale_mean=-3.4)
+    cfg = orc.make_config()
+    grp = lib.Context(devices=[0, 1, 2], max_instances=1)
+    grp.upload(scene)
+    skipped = 0
+    for k, z in enumerate([40.0, 40.0, 1.5, 40.0, 1.4]):
+        cam = _camera(W, H, (0.0, 0.0, z))
+        fb0 = np.random.default_rng(k).integers(0, 2 ** 32, size=(H, W), dtype=np.uint64).astype(np.uint32) if k % 2 else np.zeros((H, W), np.uint32)
+        got, want = fb0.copy(), fb0.copy()
+        grp.render(lib.camera_struct(cam), got)
+        orc.render(scene, orc.camera_from(cam), cfg, want)
+        assert np.array_equal(got, want), (k, int(np.count_nonzero(got != want)))
+        skipped = grp.timings()["frames_skipped"]
+        got2, want2 = np.full((H, W), 7, np.uint32), np.zeros((H, W), np.uint32)
+        grp.render_cleared(lib.camera_struct(cam), got2, 0)
+        orc.render(scene, orc.camera_from(cam), cfg, want2)
+        assert np.array_equal(got2, want2), k
+    assert skipped >= 1
+    grp.close()
