@@ -382,3 +382,62 @@ def test_group_context_repeats_abandoned_member_stripes(lib, orc):
         assert np.array_equal(got2, want2), k
     assert skipped >= 1
     grp.close()
+
+
+def test_headless_demo_writes_the_frames_the_oracle_renders(lib, orc, tmp_path):
+    """python -m splat_b200.demo (the reference's viewer loop with PNG files instead of a window), on the emulated library:
+    the PNGs decode to the oracle's RGB bytes, for a PLY (device ingest) and for the 4-Gaussian scene"""
+    import struct
+    import zlib
+
+    import numpy as np
+
+    from test_cpp_host import raw_scene
+
+    from splat_b200 import demo
+    from splat_b200.camera import Camera
+    from splat_b200.gaussians import GaussianList, naive_gaussians, save_ply
+
+    def read_png(path):
+        data = open(path, "rb").read()
+        assert data[:8] == b"\x89PNG\r\n\x1a\n"
+        pos, idat, W, H = 8, b"", 0, 0
+        while pos < len(data):
+            n, tag = struct.unpack(">I4s", data[pos:pos + 8])
+            body = data[pos + 8:pos + 8 + n]
+            assert struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(tag + body) & 0xFFFFFFFF
+            if tag == b"IHDR":
+                W, H, depth, ctype = struct.unpack(">IIBB", body[:10])
+                assert (depth, ctype) == (8, 2)
+            elif tag == b"IDAT":
+                idat += body
+            pos += 12 + n
+        rows = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(H, 1 + 3 * W)
+        assert not rows[:, 0].any()
+        return rows[:, 1:].reshape(H, W, 3)
+
+    W, H = 160, 96
+    ply = tmp_path / "s.ply"
+    save_ply(str(ply), raw_scene(1200))
+    out = tmp_path / "frames"
+    assert demo.main([str(ply), "--width", str(W), "--height", str(H), "--camera", "0", "0", "3", "--frames", "2", "--yaw-step", "0.3", "--out", str(out)]) == 0
+    ctx = lib.Context(device=0)
+    scene = ctx.upload_ply(str(ply), want_activated=True)          # the floats the device activated
+    ctx.close()
+    cam = Camera(H, W, (0.0, 0.0, 3.0))
+    for i in range(2):
+        cam.update_yaw_angle(0.3 if i else 0.0)
+        cam.update_camera_pose()
+        ref = np.zeros((H, W), np.uint32)
+        orc.render(scene, orc.camera_from(cam), orc.make_config(), ref)
+        rgb = read_png(out / f"frame_{i:04d}.png")
+        want = np.stack([(ref >> 16) & 0xFF, (ref >> 8) & 0xFF, ref & 0xFF], axis=-1).astype(np.uint8)
+        assert np.count_nonzero(ref) > 500 and np.array_equal(rgb, want)
+    out2 = tmp_path / "naive"
+    assert demo.main(["naive", "--width", "128", "--height", "80", "--pipeline", "1", "--out", str(out2)]) == 0
+    cam = Camera(80, 128, (0.0, 0.0, 3.0))
+    cam.update_camera_pose()
+    ref = np.zeros((80, 128), np.uint32)
+    orc.render(GaussianList.from_vec(naive_gaussians()), orc.camera_from(cam), orc.make_config(lowpass=0.01), ref)
+    rgb = read_png(out2 / "frame_0000.png")
+    assert np.array_equal(rgb, np.stack([(ref >> 16) & 0xFF, (ref >> 8) & 0xFF, ref & 0xFF], axis=-1).astype(np.uint8))
