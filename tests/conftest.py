@@ -13,7 +13,7 @@ def pytest_configure(config):
 
 
 # tests/test_emu_parity.py: the emulated runs that take more than a few seconds each only run on request, so that the
-# default CPU suite stays within a couple of minutes (SPLAT_EMU_FULL=1 runs all of them: about five minutes)
+# default CPU suite stays within a couple of minutes (SPLAT_EMU_FULL=1 runs all of them: about twelve minutes)
 EMU_ON_REQUEST = (
     "test_frames_without_a_host_round_trip", "test_near_cut_stripes_and_empty_regions", "test_near_cut_is_exact[128-None]",
     "test_near_cut_is_exact[512-False]", "test_a_repeated_frame_is_counted_as_retried", "test_framebuffer_bit_exact[inside_cloud]",
@@ -23,6 +23,9 @@ EMU_ON_REQUEST = (
     "test_deep_lists_exact_early_termination[deep_onto_noise]", "test_bench_two_ranks_on_the_emulated_library[async]",
     "test_group_context_equals_single_device_and_oracle_emulated[equal_stripes]",
     "test_group_context_repeats_abandoned_member_stripes",
+    # BASELINE's full sizes (281 k @720p complete; 6.1 M @1080p and 5.8 M @4K on sampled stripes): about six minutes
+    "test_config2_plush_sized_complete_frame", "test_full_size_configs_sampled_stripes[config3_bicycle_sized_1080p]",
+    "test_full_size_configs_sampled_stripes[config4_garden_sized_4k]",
     "test_cpp_viewer_loop_on_the_emulated_library[2-1-3000-320-240]", "test_cpp_viewer_loop_on_the_emulated_library[1-0-1500-200-150]",
 )
 

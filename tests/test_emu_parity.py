@@ -69,7 +69,9 @@ from test_gpu_parity import (  # noqa: E402,F401
     test_stripes_equal_full_frame,
 )
 from test_gpu_parity import (  # noqa: E402,F401
+    test_config2_plush_sized_complete_frame,
     test_deep_lists_exact_early_termination,
+    test_full_size_configs_sampled_stripes,
     test_framebuffer_bit_exact,
     test_pipeline_mirrors,
     test_projection_records_match_oracle,
