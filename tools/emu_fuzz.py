@@ -19,9 +19,10 @@ def one_case(seed, lib, orc):
     from splat_b200.gaussians import synthetic_scene
 
     rng = np.random.default_rng(seed)
-    W, H = int(rng.integers(17, 420)), int(rng.integers(17, 300))
-    n = int(rng.choice([1, 7, 300, 2000, 9000, 30000]))
-    lsm = float(rng.uniform(-4.5, -1.8))
+    big = os.environ.get("EMU_FUZZ_BIG") == "1"          # larger images and scenes: minutes per case
+    W, H = (int(rng.integers(300, 1300)), int(rng.integers(200, 760))) if big else (int(rng.integers(17, 420)), int(rng.integers(17, 300)))
+    n = int(rng.choice([20000, 80000, 250000, 600000] if big else [1, 7, 300, 2000, 9000, 30000]))
+    lsm = float(rng.uniform(-4.5, -2.6) if big else rng.uniform(-4.5, -1.8))
     scene = synthetic_scene(n, seed=0x5EED0000 + seed, log_scale_mean=lsm)
     if rng.random() < 0.3:
         scene.opacities[:] = rng.uniform(0.005, 0.08)                     # faint: pixels that never converge
