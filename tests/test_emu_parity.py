@@ -55,9 +55,7 @@ from test_gpu_parity import (  # noqa: E402,F401
     test_blends_onto_existing_contents,
     test_degenerate_inputs_are_skipped,
     test_depth_order_matches_stable_sort,
-    test_empty_scene_renders_nothing,
     test_errors_not_crashes,
-    test_everything_culled_leaves_the_buffer_untouched,
     test_euc_switches,
     test_frames_without_a_host_round_trip,
     test_near_cut_is_exact,
@@ -76,6 +74,7 @@ from test_gpu_parity import (  # noqa: E402,F401
     test_pipeline_mirrors,
     test_projection_records_match_oracle,
 )
+from test_zz_gpu_edge_cases import test_empty_scene_renders_nothing, test_everything_culled_leaves_the_buffer_untouched  # noqa: E402,F401
 from test_gpu_float import (  # noqa: E402,F401
     test_float_and_reference_blends_differ_only_by_the_truncation_bias,
     test_float_blend_matches_float_oracle,
